@@ -1,0 +1,130 @@
+/* libsg_b200 — C ABI of the B200-native shapegan hot path.
+ *
+ * The reference (marian42/shapegan) has no FFI/plugin layer: every FLOP on its hot path is issued through
+ * torch.nn modules (model/gan.py:8-23,48-57; model/progressive_gan.py:26-42; model/autoencoder.py:15-64;
+ * model/sdf_net.py:26-52).  This header is the boundary we define UNDER those classes: each entry point names the
+ * torch call it replaces.  Host code (shapegan_b200/*.py) binds it with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 for an argument/shape error (nothing launched), >0 = cudaError_t.
+ *     sg_last_error() returns a thread-local message.  Nothing here allocates, frees, synchronises or retains
+ *     pointers: all buffers (incl. workspaces) belong to the caller; work is ordered on `stream`
+ *     (a cudaStream_t passed as void*) and is CUDA-graph capturable.
+ *   - activations are NDHWC bf16 "plane" tensors: planes=1 -> plain bf16 (throughput mode); planes=2 -> hi/lo bf16
+ *     split of an fp32 value (value = hi + lo), consumed by the tensor cores as three bf16 products (fp32x mode,
+ *     the <=1e-3 parity mode).  Single-channel volumes (voxel grids) and vectors at module boundaries are fp32.
+ *   - weights live in fp32 torch layout (nn.Parameter) and are re-packed into tensor-core operand images
+ *     (K-major, 128B-swizzled, zero padded) by sg_pack_b whenever they change.
+ */
+#ifndef SG_B200_H
+#define SG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 1
+
+/* gather modes of the implicit GEMM (A operand) */
+#define SG_MODE_DENSE 0 /* rows x K contiguous (nn.Linear; k4/s1 convs on 4^3 or 1^3 grids)                    */
+#define SG_MODE_CONV 1  /* Conv3d k4 s2 p1 forward gather == ConvTranspose3d k4 s2 p1 input-gradient gather     */
+#define SG_MODE_CONVT 2 /* ConvTranspose3d k4 s2 p1 forward (8 output-parity classes) == Conv3d input gradient  */
+#define SG_MODE_PATCH 3 /* Conv3d k4 s2 p1 over a single-channel fp32 volume (first discriminator/encoder layer) */
+
+#define SG_ACT_NONE 0
+#define SG_ACT_LRELU 1 /* slope 0.2, model/gan.py:11 */
+#define SG_ACT_RELU 2
+#define SG_ACT_TANH 3
+#define SG_ACT_SIGMOID 4
+
+#define SG_OUT_BF16 0       /* bf16 planes, row stride out_ld */
+#define SG_OUT_F32 1        /* fp32 [rows][out_ld] */
+#define SG_OUT_F32_ATOMIC 2 /* fp32 atomicAdd (split-K) */
+
+typedef struct {
+  const void* ptr;      /* bf16 planes (NDHWC) or fp32 (SG_MODE_PATCH source) */
+  int64_t plane_stride; /* elements between the hi and lo plane */
+  int32_t n, d, h, w, c;
+} sg_tensor;
+
+/* out[rows, n] = act( gather(A)[rows, K] . B[n, K]^T + bias ) (* act'(mask))
+ * replaces: F.conv3d / F.conv_transpose3d / F.linear forward and input-gradient calls issued by
+ * model/gan.py:9-21,49-55, model/progressive_gan.py:28-38, model/autoencoder.py:16-63, model/sdf_net.py:27-50 */
+typedef struct {
+  int32_t mode, planes;
+  sg_tensor a;  /* source tensor */
+  sg_tensor a2; /* optional second DENSE source appended along K (ptr NULL = unused); sdf_net.py:59 skip-concat */
+  int64_t rows; /* GEMM rows (per parity class in SG_MODE_CONVT) */
+  int32_t k;    /* padded K, multiple of 64 */
+  int32_t n_pad, n_valid;
+  int32_t bn, mt, ksplit; /* tile config: N tile (mult of 16, <=256), M sub-tiles per CTA (1|2), K splits; 0 = auto */
+  const void* b_packed;   /* sg_pack_b image */
+  const float* bias;      /* [n_valid] or NULL */
+  int32_t act;
+  const void* mask; /* optional bf16 planes, same layout as out: out *= act'(mask) with mask_act */
+  int64_t mask_plane_stride;
+  int32_t mask_act;
+  void* out;
+  int64_t out_plane_stride;
+  int32_t out_kind, out_ld;
+  int32_t out_d, out_h, out_w; /* SG_MODE_CONVT: output grid (2d,2h,2w) */
+} sg_igemm_args;
+int sg_igemm(const sg_igemm_args* a, void* stream);
+
+/* dW partials: P[split][m, n] = sum_rows A[row, m] * gather(B)[row (+tap), n]
+ * replaces: the weight-gradient (bwd-filter) calls autograd issues for the layers above.
+ * A = rows x ca dense (e.g. dY), B = tensor gathered like SG_MODE_CONV (taps=64), DENSE (taps=1) or PATCH. */
+typedef struct {
+  int32_t b_mode, planes; /* SG_MODE_DENSE | SG_MODE_CONV | SG_MODE_PATCH */
+  sg_tensor a;            /* dense rows: n*d*h*w rows of c channels */
+  sg_tensor b;            /* gathered tensor */
+  int64_t rows;
+  int32_t ksplit;     /* number of row splits (0 = auto) */
+  int32_t merge_n;    /* 1: one MMA spans all N atoms (LBO stride); 0: one MMA per 64-column atom */
+  float* partials;    /* [ksplit][m_pad][n_total] fp32 workspace, m_pad = roundup(a.c,128), n_total = taps*b.c */
+  int32_t ksplit_out; /* filled by sg_wgrad_plan */
+} sg_wgrad_args;
+int sg_wgrad_plan(sg_wgrad_args* a, size_t* workspace_bytes); /* fills ksplit, returns bytes for partials */
+int sg_wgrad(const sg_wgrad_args* a, void* stream);
+
+/* Reduce wgrad partials over splits and scatter into a torch-layout fp32 gradient:
+ * grad[(m*sm + tap*st + c*sc)] (+)= sum_s P[s][m][tap*cb + c]        (m < m_valid, c < cb) */
+typedef struct {
+  const float* partials;
+  int32_t ksplit, m_pad, m_valid, taps, cb;
+  int64_t sm, st, sc;
+  float* grad;
+  int32_t accumulate; /* 1: += (torch .grad accumulation semantics) */
+  float scale;
+} sg_wgrad_reduce_args;
+int sg_wgrad_reduce(const sg_wgrad_reduce_args* a, void* stream);
+
+/* Pack fp32 torch-layout weights into the K-major swizzled operand image consumed by sg_igemm.
+ * image[class][kc][plane][n_pad][64]; logical B[n, k] with n = n1*n0_count + n0 and k = tap*kc_count + c:
+ *   src index = n1*s_n1 + n0*s_n0 + tapmap(class, tap)*s_tap + c*s_c ; zero outside (n < n_valid, c < c_valid). */
+typedef struct {
+  const float* w;
+  void* image;
+  int32_t planes, classes; /* classes = 8 selects the k4/s2/p1 transposed tap map, else 1 */
+  int32_t n_pad, n_valid, n0_count;
+  int64_t s_n1, s_n0;
+  int32_t k_pad, taps, c_count, c_valid; /* k = tap*c_count + c */
+  int64_t s_tap, s_c;
+} sg_pack_b_args;
+size_t sg_pack_b_bytes(const sg_pack_b_args* a);
+int sg_pack_b(const sg_pack_b_args* a, void* stream);
+
+/* ---- misc ---- */
+int sg_abi_version(void);
+const char* sg_last_error(void);
+int sg_device_error_word(int32_t** dev_ptr); /* device word set by a kernel watchdog (mbarrier timeout) */
+int sg_check_device_error(void);               /* diagnostic, synchronises: returns and clears that word */
+int sg_num_sms(void);
+long long sg_launch_count(void);               /* kernels launched by this library since load (bench gpu_launches) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG_B200_H */

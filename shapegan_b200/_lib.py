@@ -1,0 +1,93 @@
+"""ctypes binding of libsg_b200.so (include/sg_b200.h).  No torch types cross this boundary: only raw device
+pointers, sizes and a cudaStream_t.  The product path fails loudly when the CUDA library is missing."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_longlong, c_size_t, c_void_p
+
+from . import build as _build
+
+MODE_DENSE, MODE_CONV, MODE_CONVT, MODE_PATCH = 0, 1, 2, 3
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
+
+
+class SgTensor(ctypes.Structure):
+    _fields_ = [('ptr', c_void_p), ('plane_stride', c_int64),
+                ('n', c_int32), ('d', c_int32), ('h', c_int32), ('w', c_int32), ('c', c_int32)]
+
+
+class SgIgemmArgs(ctypes.Structure):
+    _fields_ = [('mode', c_int32), ('planes', c_int32), ('a', SgTensor), ('a2', SgTensor), ('rows', c_int64),
+                ('k', c_int32), ('n_pad', c_int32), ('n_valid', c_int32),
+                ('bn', c_int32), ('mt', c_int32), ('ksplit', c_int32),
+                ('b_packed', c_void_p), ('bias', c_void_p), ('act', c_int32),
+                ('mask', c_void_p), ('mask_plane_stride', c_int64), ('mask_act', c_int32),
+                ('out', c_void_p), ('out_plane_stride', c_int64), ('out_kind', c_int32), ('out_ld', c_int32),
+                ('out_d', c_int32), ('out_h', c_int32), ('out_w', c_int32)]
+
+
+class SgWgradArgs(ctypes.Structure):
+    _fields_ = [('b_mode', c_int32), ('planes', c_int32), ('a', SgTensor), ('b', SgTensor), ('rows', c_int64),
+                ('ksplit', c_int32), ('merge_n', c_int32), ('partials', c_void_p), ('ksplit_out', c_int32)]
+
+
+class SgWgradReduceArgs(ctypes.Structure):
+    _fields_ = [('partials', c_void_p), ('ksplit', c_int32), ('m_pad', c_int32), ('m_valid', c_int32),
+                ('taps', c_int32), ('cb', c_int32), ('sm', c_int64), ('st', c_int64), ('sc', c_int64),
+                ('grad', c_void_p), ('accumulate', c_int32), ('scale', c_float)]
+
+
+class SgPackBArgs(ctypes.Structure):
+    _fields_ = [('w', c_void_p), ('image', c_void_p), ('planes', c_int32), ('classes', c_int32),
+                ('n_pad', c_int32), ('n_valid', c_int32), ('n0_count', c_int32), ('s_n1', c_int64), ('s_n0', c_int64),
+                ('k_pad', c_int32), ('taps', c_int32), ('c_count', c_int32), ('c_valid', c_int32),
+                ('s_tap', c_int64), ('s_c', c_int64)]
+
+
+# every symbol include/sg_b200.h declares, with (restype, argtypes); tests check that all of them resolve
+SYMBOLS = {
+    'sg_abi_version': (c_int32, []),
+    'sg_last_error': (c_char_p, []),
+    'sg_device_error_word': (c_int32, [ctypes.POINTER(c_void_p)]),
+    'sg_check_device_error': (c_int32, []),
+    'sg_num_sms': (c_int32, []),
+    'sg_launch_count': (c_longlong, []),
+    'sg_igemm': (c_int32, [ctypes.POINTER(SgIgemmArgs), c_void_p]),
+    'sg_wgrad_plan': (c_int32, [ctypes.POINTER(SgWgradArgs), ctypes.POINTER(c_size_t)]),
+    'sg_wgrad': (c_int32, [ctypes.POINTER(SgWgradArgs), c_void_p]),
+    'sg_wgrad_reduce': (c_int32, [ctypes.POINTER(SgWgradReduceArgs), c_void_p]),
+    'sg_pack_b_bytes': (c_size_t, [ctypes.POINTER(SgPackBArgs)]),
+    'sg_pack_b': (c_int32, [ctypes.POINTER(SgPackBArgs), c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (building if stale and nvcc is available) the in-tree shared library.  Raises if it cannot be loaded:
+    there is no CPU or eager-PyTorch fallback for the hot path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or (os.path.exists(_build.NVCC) and os.environ.get('SG_B200_NO_REBUILD') != '1'):
+        if os.path.exists(_build.NVCC):
+            path = _build.build_lib()
+    if not os.path.exists(path):
+        raise RuntimeError('libsg_b200.so is missing (%s) and nvcc is unavailable: the shapegan_b200 hot path has no '
+                           'fallback. Run `python -m shapegan_b200.build`.' % path)
+    h = ctypes.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(h, name)           # AttributeError here == ABI mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if h.sg_abi_version() != 1:
+        raise RuntimeError('libsg_b200 ABI version mismatch')
+    _lib = h
+    return h
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().sg_last_error()
+        raise RuntimeError('libsg_b200 %s failed (%d): %s' % (what, rc, msg.decode() if msg else '?'))

@@ -1,0 +1,494 @@
+// Implicit-GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM) for every dense contraction of
+// the shapegan hot path: Conv3d / ConvTranspose3d (k4,s2,p1) forward + input gradient, nn.Linear, and the
+// weight-gradient GEMMs.  One persistent, warp-specialised CTA per SM:
+//
+//   warps 0-3  producers   A operand: 16-byte cp.async gathers from NDHWC bf16 planes straight into the
+//                          128B-swizzled K-major (or MN-major for wgrad) UMMA layout, zero-filled padding;
+//                          B operand (pre-packed weights): 1-D TMA bulk copies (cp.async.bulk) on an mbarrier.
+//   warp  4    MMA issuer  one thread issues tcgen05.mma (M=128, N=bn, K=16) and tcgen05.commit.
+//   warps 5-8  epilogue    tcgen05.ld TMEM -> registers -> bias / activation / mask -> bf16 planes or fp32.
+//
+// fp32x mode (planes=2) feeds hi/lo bf16 splits and issues three MMAs per K step (hi*hi + hi*lo + lo*hi).
+#include <algorithm>
+#include <cstring>
+
+#include "sg_common.cuh"
+#include "sg_internal.h"
+
+namespace sg {
+
+constexpr int kProducerThreads = 128;
+constexpr int kIgemmThreads = 288;      // 4 producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int kMaxStages = 6;
+constexpr int kSmemHeader = 1024;       // barriers + tmem pointer
+
+struct IgemmP {
+  int mode, planes;
+  const char* a_ptr; long long a_ps; int aN, aD, aH, aW, aC;
+  const char* a2_ptr; long long a2_ps; int a2C;
+  long long rows; int kchunks, n_pad, n_valid, bn, mt, ksplit, classes;
+  const char* b;
+  const float* bias; int act;
+  const bf16* mask; long long mask_ps; int mask_act;
+  char* out; long long out_ps; int out_kind, out_ld, oD, oH, oW;
+  int stages, m_tiles, n_tiles; long long work_total;
+  int acc_bufs, acc_slot;
+  unsigned ktab_bytes, stage_bytes, a_stage_bytes;
+  int* err;
+};
+
+struct SmemHeader {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t accfull[2];
+  uint64_t accempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void decode_work(const IgemmP& p, long long w, int& cls, int& nt, int& mtile, int& ks) {
+  ks = (int)(w % p.ksplit); w /= p.ksplit;
+  mtile = (int)(w % p.m_tiles); w /= p.m_tiles;
+  nt = (int)(w % p.n_tiles);
+  cls = (int)(w / p.n_tiles);
+}
+
+__global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid_constant__ IgemmP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+  uint32_t* ktab = reinterpret_cast<uint32_t*>(smem + kSmemHeader);
+  uint8_t* stage0 = smem + kSmemHeader + p.ktab_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], kProducerThreads + 1); mbar_init(&hdr->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(&hdr->tmem_base, 512);
+  if (p.mode == SG_MODE_CONV || p.mode == SG_MODE_CONVT) {
+    // ktab[k/8] = channel | tap offsets; K index k = tap*C + c (c fastest)
+    const int n8 = p.kchunks * 8;
+    for (int i = tid; i < n8; i += kIgemmThreads) {
+      int k = i * 8, tap = k / p.aC, c = k - tap * p.aC;
+      uint32_t dd, dh, dw;
+      if (p.mode == SG_MODE_CONV) { dd = tap >> 4; dh = (tap >> 2) & 3; dw = tap & 3; }
+      else { dd = tap >> 2; dh = (tap >> 1) & 1; dw = tap & 1; }
+      ktab[i] = (uint32_t)c | (dd << 16) | (dh << 19) | (dw << 22);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+  if ((smem_u32(smem) & 1023u) != 0) {       // swizzled operand tiles need a 1024-byte aligned base
+    if (tid == 0) atomicExch(p.err, kErrSmemAlign);
+    __trap();
+  }
+
+  const int cps = (p.kchunks + p.ksplit - 1) / p.ksplit;   // K chunks per split
+
+  if (warp < 4) {
+    // ================================================================ PRODUCERS
+    const int g = tid & 7, rb = tid >> 3;
+    int s = 0; uint32_t ph = 0;
+    int prev_s = -1;
+    const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+      int cls, nt, mtile, ks;
+      decode_work(p, w, cls, nt, mtile, ks);
+      const int pd = (cls >> 2) & 1, phh = (cls >> 1) & 1, pw = cls & 1;
+      // per-thread row descriptors: 8 rows per M sub-tile
+      int ri_n[2][8]; uint32_t ri_c[2][8];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ri_n[sub][i] = -1; ri_c[sub][i] = 0;
+          if (sub < p.mt) {
+            long long gr = ((long long)mtile * p.mt + sub) * kTileRows + rb + 16 * i;
+            if (gr < p.rows) {
+              if (p.mode == SG_MODE_DENSE) {
+                ri_n[sub][i] = (int)gr;
+              } else if (p.mode == SG_MODE_CONVT) {
+                int qw = (int)(gr % p.aW); long long t = gr / p.aW;
+                int qh = (int)(t % p.aH); t /= p.aH;
+                int qd = (int)(t % p.aD); int n = (int)(t / p.aD);
+                ri_n[sub][i] = n * p.aD * p.aH * p.aW;
+                ri_c[sub][i] = (uint32_t)(qd + 1) | ((uint32_t)(qh + 1) << 10) | ((uint32_t)(qw + 1) << 20);
+              } else {  // CONV / PATCH: rows enumerate the stride-2 output grid
+                const int oW = p.aW >> 1, oH = p.aH >> 1, oD = p.aD >> 1;
+                int ow = (int)(gr % oW); long long t = gr / oW;
+                int oh = (int)(t % oH); t /= oH;
+                int od = (int)(t % oD); int n = (int)(t / oD);
+                ri_n[sub][i] = n * p.aD * p.aH * p.aW;
+                ri_c[sub][i] = (uint32_t)(2 * od) | ((uint32_t)(2 * oh) << 10) | ((uint32_t)(2 * ow) << 20);  // (2o-1)+1
+              }
+            }
+          }
+        }
+      }
+      const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
+      for (int kc = k0; kc < k1; ++kc) {
+        mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+        uint8_t* st = stage0 + (size_t)s * p.stage_bytes;
+        const uint32_t a_base = smem_u32(st);
+        if (p.mode == SG_MODE_PATCH) {
+          // single-channel fp32 volume: K = 64 taps, piece g = taps [8g, 8g+8) = (kd = g>>1, kh = 2(g&1)+{0,1}, kw = 0..3)
+          const float* vol = reinterpret_cast<const float*>(p.a_ptr);
+          const int kd = g >> 1, khb = (g & 1) * 2;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub >= p.mt) break;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = 0.f;
+              if (ri_n[sub][i] >= 0) {
+                const uint32_t c = ri_c[sub][i];
+                const int d = (int)(c & 1023) - 1 + kd;
+                const int w0 = (int)((c >> 20) & 1023) - 1;
+                if (d >= 0 && d < p.aD) {
+#pragma unroll
+                  for (int hh = 0; hh < 2; ++hh) {
+                    const int h = (int)((c >> 10) & 1023) - 1 + khb + hh;
+                    if (h >= 0 && h < p.aH) {
+                      const float* rowp = vol + (size_t)ri_n[sub][i] + ((size_t)d * p.aH + h) * p.aW;
+#pragma unroll
+                      for (int ww = 0; ww < 4; ++ww) {
+                        const int x = w0 + ww;
+                        if (x >= 0 && x < p.aW) v[hh * 4 + ww] = __ldg(rowp + x);
+                      }
+                    }
+                  }
+                }
+              }
+              const uint32_t row = rb + 16 * i;
+              uint4 hi;
+              hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+              hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+              uint8_t* tile = st + (size_t)(sub * p.planes) * kTileBytes;
+              *reinterpret_cast<uint4*>(tile + sw128(row, g)) = hi;
+              if (p.planes == 2) {
+                uint4 lo;
+                lo.x = pack_bf16x2(v[0] - bf16lo_to_f(hi.x), v[1] - bf16hi_to_f(hi.x));
+                lo.y = pack_bf16x2(v[2] - bf16lo_to_f(hi.y), v[3] - bf16hi_to_f(hi.y));
+                lo.z = pack_bf16x2(v[4] - bf16lo_to_f(hi.z), v[5] - bf16hi_to_f(hi.z));
+                lo.w = pack_bf16x2(v[6] - bf16lo_to_f(hi.w), v[7] - bf16hi_to_f(hi.w));
+                *reinterpret_cast<uint4*>(tile + kTileBytes + sw128(row, g)) = lo;
+              }
+            }
+          }
+        } else {
+          // bf16 plane gathers
+          const char* src_base; long long src_ps; int rowC, coff;
+          int dd = 0, dh = 0, dw = 0;
+          if (p.mode == SG_MODE_DENSE) {
+            const int c1chunks = p.aC >> 6;
+            if (kc < c1chunks) { src_base = p.a_ptr; src_ps = p.a_ps; rowC = p.aC; coff = kc * 64 + g * 8; }
+            else { src_base = p.a2_ptr; src_ps = p.a2_ps; rowC = p.a2C; coff = (kc - c1chunks) * 64 + g * 8; }
+          } else {
+            const uint32_t e = ktab[kc * 8 + g];
+            src_base = p.a_ptr; src_ps = p.a_ps; rowC = p.aC; coff = (int)(e & 0xffff);
+            dd = (int)((e >> 16) & 7); dh = (int)((e >> 19) & 7); dw = (int)((e >> 22) & 7);
+            if (p.mode == SG_MODE_CONVT) { dd = pd ? 1 - dd : -dd; dh = phh ? 1 - dh : -dh; dw = pw ? 1 - dw : -dw; }
+          }
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub >= p.mt) break;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              long long off = 0; uint32_t nbytes = 0;
+              if (ri_n[sub][i] >= 0) {
+                if (p.mode == SG_MODE_DENSE) {
+                  off = (long long)ri_n[sub][i] * rowC + coff; nbytes = 16;
+                } else {
+                  const uint32_t c = ri_c[sub][i];
+                  const int d = (int)(c & 1023) - 1 + dd, h = (int)((c >> 10) & 1023) - 1 + dh, x = (int)((c >> 20) & 1023) - 1 + dw;
+                  if (d >= 0 && d < p.aD && h >= 0 && h < p.aH && x >= 0 && x < p.aW) {
+                    off = ((long long)ri_n[sub][i] + ((long long)d * p.aH + h) * p.aW + x) * rowC + coff; nbytes = 16;
+                  }
+                }
+              }
+              const uint32_t row = rb + 16 * i;
+              const uint32_t dst = a_base + (uint32_t)(sub * p.planes) * kTileBytes + sw128(row, g);
+              cp_async16(dst, src_base + off * 2, nbytes);
+              if (p.planes == 2) cp_async16(dst + kTileBytes, src_base + (off + src_ps) * 2, nbytes);
+            }
+          }
+        }
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&hdr->full[s], b_tile_bytes * p.planes);
+          const uint32_t b_dst = a_base + p.a_stage_bytes;
+          for (int pl = 0; pl < p.planes; ++pl) {
+            const char* src = p.b + ((((size_t)cls * p.kchunks + kc) * p.planes + pl) * p.n_pad + (size_t)nt * p.bn) * 128;
+            bulk_g2s(b_dst + pl * b_tile_bytes, src, b_tile_bytes, &hdr->full[s]);
+          }
+        }
+        cp_async_commit();
+        if (prev_s >= 0) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&hdr->full[prev_s]); }
+        prev_s = s;
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+    if (prev_s >= 0) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&hdr->full[prev_s]); }
+  } else if (warp == 4) {
+    // ================================================================ MMA ISSUER
+    const uint32_t idesc = umma_idesc(128, p.bn, false, false);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
+      int cls, nt, mtile, ks;
+      decode_work(p, w, cls, nt, mtile, ks);
+      const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
+      const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
+      mbar_wait(&hdr->accempty[ab], aph ^ 1, p.err);
+      tc_fence_after();
+      const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
+      for (int kc = k0; kc < k1; ++kc) {
+        mbar_wait(&hdr->full[s], ph, p.err);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
+          const uint32_t b_base = a_base + p.a_stage_bytes;
+          const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+          for (int sub = 0; sub < p.mt; ++sub) {
+            const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
+            const uint32_t a_hi = a_base + (uint32_t)(sub * p.planes) * kTileBytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = umma_desc(a_hi + kk * 32, 16, 1024);
+              const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
+              umma_bf16(d_addr, da, db, idesc, (kc > k0 || kk > 0) ? 1u : 0u);
+              if (p.planes == 2) {
+                const uint64_t da_lo = umma_desc(a_hi + kTileBytes + kk * 32, 16, 1024);
+                const uint64_t db_lo = umma_desc(b_base + b_tile_bytes + kk * 32, 16, 1024);
+                umma_bf16(d_addr, da, db_lo, idesc, 1u);
+                umma_bf16(d_addr, da_lo, db, idesc, 1u);
+              }
+            }
+          }
+          umma_commit(&hdr->empty[s]);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (lane == 0) umma_commit(&hdr->accfull[ab]);
+      __syncwarp();
+    }
+  } else {
+    // ================================================================ EPILOGUE
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int trow = q * 32 + lane;
+    int it = 0;
+    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
+      int cls, nt, mtile, ks;
+      decode_work(p, w, cls, nt, mtile, ks);
+      const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
+      const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
+      mbar_wait(&hdr->accfull[ab], aph, p.err);
+      tc_fence_after();
+      const bool add_bias = (p.bias != nullptr) && (ks == 0);
+      for (int sub = 0; sub < p.mt; ++sub) {
+        const long long gr = ((long long)mtile * p.mt + sub) * kTileRows + trow;
+        const bool valid = gr < p.rows;
+        long long orow = gr;
+        if (p.mode == SG_MODE_CONVT && valid) {
+          int qw = (int)(gr % p.aW); long long t = gr / p.aW;
+          int qh = (int)(t % p.aH); t /= p.aH;
+          int qd = (int)(t % p.aD); long long n = t / p.aD;
+          orow = ((n * p.oD + 2 * qd + ((cls >> 2) & 1)) * p.oH + 2 * qh + ((cls >> 1) & 1)) * p.oW + 2 * qw + (cls & 1);
+        }
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t r[32];
+          __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
+          if (c0 + 32 <= p.bn) {
+            tmem_ld32(t_addr + c0, r);
+          } else {
+            uint32_t r16[16];
+            tmem_ld16(t_addr + c0, r16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0; }
+          }
+          tmem_ld_wait();
+          if (!valid) continue;
+          const int nb = nt * p.bn + c0;
+          const int ncols = min(32, p.bn - c0);
+#pragma unroll
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            if (j8 >= ncols) break;
+            const int n = nb + j8;
+            if (n >= p.n_valid) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = __uint_as_float(r[j8 + j]);
+              if (add_bias && n + j < p.n_valid) x += __ldg(p.bias + n + j);
+              v[j] = apply_act(x, p.act);
+            }
+            const long long eoff = orow * p.out_ld + n;
+            const bool full8 = (n + 8 <= p.n_valid);
+            if (p.mask) {
+              if (full8 && (p.out_ld & 7) == 0) {
+                const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask + eoff));
+                v[0] *= act_grad_from_output(bf16lo_to_f(m.x), p.mask_act); v[1] *= act_grad_from_output(bf16hi_to_f(m.x), p.mask_act);
+                v[2] *= act_grad_from_output(bf16lo_to_f(m.y), p.mask_act); v[3] *= act_grad_from_output(bf16hi_to_f(m.y), p.mask_act);
+                v[4] *= act_grad_from_output(bf16lo_to_f(m.z), p.mask_act); v[5] *= act_grad_from_output(bf16hi_to_f(m.z), p.mask_act);
+                v[6] *= act_grad_from_output(bf16lo_to_f(m.w), p.mask_act); v[7] *= act_grad_from_output(bf16hi_to_f(m.w), p.mask_act);
+              } else {
+                for (int j = 0; j < 8 && n + j < p.n_valid; ++j)
+                  v[j] *= act_grad_from_output(__bfloat162float(p.mask[eoff + j]), p.mask_act);
+              }
+            }
+            if (p.out_kind == SG_OUT_BF16) {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + eoff;
+              if (full8 && (p.out_ld & 7) == 0) {
+                uint4 hi;
+                hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(o) = hi;
+                if (p.planes == 2) {
+                  uint4 lo;
+                  lo.x = pack_bf16x2(v[0] - bf16lo_to_f(hi.x), v[1] - bf16hi_to_f(hi.x));
+                  lo.y = pack_bf16x2(v[2] - bf16lo_to_f(hi.y), v[3] - bf16hi_to_f(hi.y));
+                  lo.z = pack_bf16x2(v[4] - bf16lo_to_f(hi.z), v[5] - bf16hi_to_f(hi.z));
+                  lo.w = pack_bf16x2(v[6] - bf16lo_to_f(hi.w), v[7] - bf16hi_to_f(hi.w));
+                  *reinterpret_cast<uint4*>(o + p.out_ps) = lo;
+                }
+              } else {
+                for (int j = 0; j < 8 && n + j < p.n_valid; ++j) {
+                  const bf16 h = __float2bfloat16_rn(v[j]);
+                  o[j] = h;
+                  if (p.planes == 2) o[p.out_ps + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+                }
+              }
+            } else if (p.out_kind == SG_OUT_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + eoff;
+              if (full8 && (p.out_ld & 3) == 0) {
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                for (int j = 0; j < 8 && n + j < p.n_valid; ++j) o[j] = v[j];
+              }
+            } else {
+              float* o = reinterpret_cast<float*>(p.out) + eoff;
+              for (int j = 0; j < 8 && n + j < p.n_valid; ++j) atomicAdd(o + j, v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&hdr->accempty[ab]);
+    }
+  }
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================ host launcher
+static int igemm_validate(const sg_igemm_args* a) {
+  if (!a) return sg_fail(-1, "sg_igemm: null args");
+  if (a->planes != 1 && a->planes != 2) return sg_fail(-2, "sg_igemm: planes must be 1 or 2");
+  if (a->mode < 0 || a->mode > 3) return sg_fail(-3, "sg_igemm: bad mode");
+  if (a->k <= 0 || (a->k & 63)) return sg_fail(-4, "sg_igemm: K must be a positive multiple of 64");
+  if (a->n_pad <= 0 || (a->n_pad & 15) || a->n_valid <= 0 || a->n_valid > a->n_pad) return sg_fail(-5, "sg_igemm: bad N");
+  if (a->rows < 0) return sg_fail(-6, "sg_igemm: negative rows");
+  if (!a->a.ptr || !a->b_packed || !a->out) return sg_fail(-7, "sg_igemm: null tensor");
+  if (a->mode == SG_MODE_DENSE) {
+    int kk = a->a.c + (a->a2.ptr ? a->a2.c : 0);
+    if (kk != a->k) return sg_fail(-8, "sg_igemm: DENSE needs K == a.c (+ a2.c)");
+    if (a->a2.ptr && ((a->a.c & 63) || (a->a2.c & 63))) return sg_fail(-9, "sg_igemm: two-source DENSE needs 64-multiples");
+  } else if (a->mode == SG_MODE_CONV) {
+    if ((a->a.c & 7) || a->k != 64 * a->a.c) return sg_fail(-10, "sg_igemm: CONV needs C%8==0 and K==64*C");
+    if ((a->a.d | a->a.h | a->a.w) & 1) return sg_fail(-11, "sg_igemm: CONV needs even dims");
+  } else if (a->mode == SG_MODE_CONVT) {
+    if ((a->a.c & 7) || a->k != 8 * a->a.c) return sg_fail(-12, "sg_igemm: CONVT needs C%8==0 and K==8*C");
+    if (a->out_d != 2 * a->a.d || a->out_h != 2 * a->a.h || a->out_w != 2 * a->a.w) return sg_fail(-13, "sg_igemm: CONVT out dims");
+  } else {
+    if (a->a.c != 1 || a->k != 64) return sg_fail(-14, "sg_igemm: PATCH needs C==1, K==64");
+    if ((a->a.d | a->a.h | a->a.w) & 1) return sg_fail(-11, "sg_igemm: PATCH needs even dims");
+  }
+  if (a->a.d > 1000 || a->a.h > 1000 || a->a.w > 1000) return sg_fail(-15, "sg_igemm: dims too large");
+  if (a->out_kind < 0 || a->out_kind > 2) return sg_fail(-16, "sg_igemm: bad out_kind");
+  return 0;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
+  int rc = igemm_validate(a);
+  if (rc) return rc;
+  if (a->rows == 0) return 0;
+  IgemmP p;
+  memset(&p, 0, sizeof(p));
+  p.mode = a->mode; p.planes = a->planes;
+  p.a_ptr = (const char*)a->a.ptr; p.a_ps = a->a.plane_stride;
+  p.aN = a->a.n; p.aD = a->a.d; p.aH = a->a.h; p.aW = a->a.w; p.aC = a->a.c;
+  p.a2_ptr = (const char*)a->a2.ptr; p.a2_ps = a->a2.plane_stride; p.a2C = a->a2.c;
+  p.rows = a->rows; p.kchunks = a->k / 64; p.n_pad = a->n_pad; p.n_valid = a->n_valid;
+  p.classes = (a->mode == SG_MODE_CONVT) ? 8 : 1;
+  p.b = (const char*)a->b_packed; p.bias = a->bias; p.act = a->act;
+  p.mask = (const bf16*)a->mask; p.mask_ps = a->mask_plane_stride; p.mask_act = a->mask_act;
+  p.out = (char*)a->out; p.out_ps = a->out_plane_stride; p.out_kind = a->out_kind; p.out_ld = a->out_ld;
+  p.oD = a->out_d; p.oH = a->out_h; p.oW = a->out_w;
+  p.err = sg_error_word();
+
+  const int sms = sg_num_sms();
+  const long long row_tiles = (a->rows + 127) / 128;
+  // ---- tile configuration
+  int bn = a->bn, mt = a->mt, ksplit = a->ksplit;
+  if (bn <= 0) {
+    bn = a->n_pad;
+    if (bn > 256) {                       // largest divisor of n_pad that is a multiple of 16 and <= 256
+      bn = 256;
+      while (a->n_pad % bn) bn -= 16;
+    }
+    // not enough work for the machine: narrow the N tile (keeps tensor throughput, multiplies CTAs)
+    while (bn > 64 && (bn % 32) == 0 && row_tiles * p.classes * (a->n_pad / bn) < sms) bn /= 2;
+  }
+  if (bn > 256 || (bn & 15) || a->n_pad % bn) return sg_fail(-20, "sg_igemm: bad bn");
+  const int n_tiles = a->n_pad / bn;
+  if (mt <= 0) mt = (row_tiles * p.classes * n_tiles >= 2LL * sms && bn * 2 <= 512) ? 2 : 1;
+  if (mt < 1 || mt > 2 || mt * bn > 512) return sg_fail(-21, "sg_igemm: bad mt");
+  if (ksplit <= 0) ksplit = 1;
+  if (ksplit > p.kchunks) ksplit = p.kchunks;
+  if (ksplit > 1 && a->out_kind != SG_OUT_F32_ATOMIC) return sg_fail(-22, "sg_igemm: split-K needs SG_OUT_F32_ATOMIC");
+  {  // no empty split
+    int cps = (p.kchunks + ksplit - 1) / ksplit;
+    ksplit = (p.kchunks + cps - 1) / cps;
+  }
+  p.bn = bn; p.mt = mt; p.ksplit = ksplit;
+  p.n_tiles = n_tiles;
+  p.m_tiles = (int)((row_tiles + mt - 1) / mt);
+  p.work_total = (long long)p.classes * n_tiles * p.m_tiles * ksplit;
+  p.acc_slot = (bn + 31) & ~31;
+  p.acc_bufs = (2 * mt * p.acc_slot <= 512) ? 2 : 1;
+  p.a_stage_bytes = (unsigned)(mt * a->planes * kTileBytes);
+  p.stage_bytes = p.a_stage_bytes + (unsigned)(a->planes * bn * 128);
+  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  p.ktab_bytes = (a->mode == SG_MODE_CONV || a->mode == SG_MODE_CONVT) ? (unsigned)((p.kchunks * 8 * 4 + 1023) & ~1023) : 0u;
+  const unsigned budget = 227u * 1024u - kSmemHeader - p.ktab_bytes;
+  int stages = (int)(budget / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return sg_fail(-23, "sg_igemm: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sg_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = (int)std::min<long long>(p.work_total, sms);
+  sg_igemm_kernel<<<grid, kIgemmThreads, smem, (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+  sg_count_launch();
+  return 0;
+}

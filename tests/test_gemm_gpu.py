@@ -1,0 +1,205 @@
+"""GPU (-m gpu): unit parity of the tcgen05 implicit-GEMM / wgrad kernels through the C ABI, against torch fp64
+math on the SAME bf16-rounded operands (so the only difference is fp32 accumulation order: tolerance 2e-5 relative
+to the output's max-abs for fp32 outputs; bf16 outputs add one rounding, 2^-8).  fp32x (planes=2) is compared
+with fp64 math on the UNROUNDED fp32 operands: the hi/lo split must recover fp32 accuracy (1e-5)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 2e-5
+TOL_BF16 = 6e-3
+
+
+def _imports():
+    from shapegan_b200 import _lib as L
+    from shapegan_b200 import raw
+    return L, raw
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(shape, generator=g) * 2 - 1) * scale).cuda()
+
+
+def q(x, planes):
+    """operand as the kernel sees it"""
+    return x.to(torch.bfloat16).double() if planes == 1 else x.double()
+
+
+def report(name, got, ref, tol):
+    got, ref = got.double(), ref.double()
+    scale = ref.abs().max().item() + 1e-30
+    err = (got - ref).abs()
+    m = err.max().item() / scale
+    if m > tol:
+        bad = (err / scale > tol)
+        idx = bad.nonzero()
+        print('\n[%s] FAIL rel-max-err %.3e tol %.1e; %d/%d bad; first bad %s; got %s ref %s' % (
+            name, m, tol, bad.sum().item(), bad.numel(), idx[0].tolist(), got[tuple(idx[0])].item(), ref[tuple(idx[0])].item()))
+        # row / column structure of the failure helps localise layout bugs
+        if got.dim() == 2:
+            print('   bad rows:', bad.any(1).nonzero().flatten()[:16].tolist(), 'bad cols:', bad.any(0).nonzero().flatten()[:16].tolist())
+    assert m <= tol, '%s: rel-max-err %.3e > %.1e' % (name, m, tol)
+    return m
+
+
+def check_error_word():
+    L, raw = _imports()
+    torch.cuda.synchronize()
+    assert L.lib().sg_check_device_error() == 0
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+@pytest.mark.parametrize('rows,k,n,bn,mt', [(300, 192, 256, 0, 0), (128, 64, 16, 0, 0), (1000, 256, 256, 256, 2),
+                                            (77, 128, 48, 0, 1), (4096, 512, 128, 64, 2), (5, 16384, 128, 0, 0)])
+def test_dense(planes, rows, k, n, bn, mt):
+    L, raw = _imports()
+    x = rnd((rows, k), 1)
+    w = rnd((n, k), 2, 0.1)
+    bias = rnd((n,), 3)
+    xp = raw.to_planes(x, planes)
+    img = raw.pack_linear(w, planes)
+    out = torch.empty((rows, n), dtype=torch.float32, device='cuda')
+    raw.igemm(L.MODE_DENSE, planes, xp, (1, 1, 1, 1, k), rows, k, img, n, out, n, out_kind=L.OUT_F32, bias=bias, bn=bn, mt=mt)
+    ref = q(x, planes) @ q(w, planes).t() + bias.double()
+    report('dense p%d %s' % (planes, (rows, k, n)), out, ref, TOL_F32)
+    # bf16 plane output + activation
+    outp = torch.empty((planes, rows, n), dtype=torch.bfloat16, device='cuda')
+    raw.igemm(L.MODE_DENSE, planes, xp, (1, 1, 1, 1, k), rows, k, img, n, outp, n, bias=bias, act=L.ACT_LRELU, bn=bn, mt=mt)
+    report('dense-bf16 p%d' % planes, raw.from_planes(outp), F.leaky_relu(ref, 0.2), TOL_BF16 if planes == 1 else 1e-4)
+    check_error_word()
+
+
+def test_dense_two_sources_and_splitk():
+    L, raw = _imports()
+    rows = 500
+    x1, x2 = rnd((rows, 256), 1), rnd((rows, 192), 2)
+    w = rnd((256, 448), 3, 0.1)
+    for planes in (1, 2):
+        img = raw.pack_linear(w, planes)
+        out = torch.empty((rows, 256), dtype=torch.float32, device='cuda')
+        raw.igemm(L.MODE_DENSE, planes, raw.to_planes(x1, planes), (1, 1, 1, 1, 256), rows, 448, img, 256, out, 256,
+                  out_kind=L.OUT_F32, a2=raw.to_planes(x2, planes), a2_c=192)
+        ref = torch.cat((q(x1, planes), q(x2, planes)), 1) @ q(w, planes).t()
+        report('dense-2src p%d' % planes, out, ref, TOL_F32)
+    # split-K with atomics
+    x = rnd((20, 16384), 4)
+    w = rnd((128, 16384), 5, 0.05)
+    bias = rnd((128,), 6)
+    out = torch.zeros((20, 128), dtype=torch.float32, device='cuda')
+    raw.igemm(L.MODE_DENSE, 1, raw.to_planes(x, 1), (1, 1, 1, 1, 16384), 20, 16384, raw.pack_linear(w, 1), 128, out, 128,
+              out_kind=L.OUT_F32_ATOMIC, bias=bias, ksplit=64)
+    report('dense-splitk', out, q(x, 1) @ q(w, 1).t() + bias.double(), TOL_F32)
+    check_error_word()
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+@pytest.mark.parametrize('b,r,cin,cout', [(2, 8, 64, 128), (3, 16, 32, 64), (2, 8, 24, 48), (1, 4, 128, 256), (2, 8, 96, 16)])
+def test_conv_fwd(planes, b, r, cin, cout):
+    L, raw = _imports()
+    x = rnd((b, r, r, r, cin), 1)                       # NDHWC
+    w = rnd((cout, cin, 4, 4, 4), 2, 0.05)
+    bias = rnd((cout,), 3)
+    ro = r // 2
+    rows = b * ro ** 3
+    out = torch.empty((rows, cout), dtype=torch.float32, device='cuda')
+    raw.igemm(L.MODE_CONV, planes, raw.to_planes(x, planes), (b, r, r, r, cin), rows, 64 * cin, raw.pack_conv_fwd(w, planes),
+              cout, out, cout, out_kind=L.OUT_F32, bias=bias)
+    ref = F.conv3d(q(x, planes).permute(0, 4, 1, 2, 3), q(w, planes), bias.double(), stride=2, padding=1)
+    report('conv p%d %s' % (planes, (b, r, cin, cout)), out, ref.permute(0, 2, 3, 4, 1).reshape(rows, cout), TOL_F32)
+    check_error_word()
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+@pytest.mark.parametrize('b,r,cin,cout', [(2, 4, 64, 32), (3, 8, 128, 64), (2, 4, 256, 128), (1, 8, 48, 24)])
+def test_convt_fwd(planes, b, r, cin, cout):
+    L, raw = _imports()
+    x = rnd((b, r, r, r, cin), 1)
+    w = rnd((cin, cout, 4, 4, 4), 2, 0.05)              # ConvTranspose3d layout
+    bias = rnd((cout,), 3)
+    ro = 2 * r
+    out = torch.zeros((b * ro ** 3, cout), dtype=torch.float32, device='cuda')
+    raw.igemm(L.MODE_CONVT, planes, raw.to_planes(x, planes), (b, r, r, r, cin), b * r ** 3, 8 * cin,
+              raw.pack_convt_fwd(w, planes), cout, out, cout, out_kind=L.OUT_F32, bias=bias, out_dims=(ro, ro, ro))
+    ref = F.conv_transpose3d(q(x, planes).permute(0, 4, 1, 2, 3), q(w, planes), bias.double(), stride=2, padding=1)
+    report('convt p%d %s' % (planes, (b, r, cin, cout)), out, ref.permute(0, 2, 3, 4, 1).reshape(-1, cout), TOL_F32)
+    check_error_word()
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+def test_conv_dgrad_and_convt_dgrad(planes):
+    L, raw = _imports()
+    # Conv3d input gradient == MODE_CONVT over dY with the conv weight
+    b, r, cin, cout = 2, 8, 32, 64
+    w = rnd((cout, cin, 4, 4, 4), 1, 0.05)
+    dy = rnd((b, r // 2, r // 2, r // 2, cout), 2)
+    out = torch.zeros((b * r ** 3, cin), dtype=torch.float32, device='cuda')
+    raw.igemm(L.MODE_CONVT, planes, raw.to_planes(dy, planes), (b, r // 2, r // 2, r // 2, cout), b * (r // 2) ** 3, 8 * cout,
+              raw.pack_conv_dgrad(w, planes), cin, out, cin, out_kind=L.OUT_F32, out_dims=(r, r, r))
+    ref = F.conv_transpose3d(q(dy, planes).permute(0, 4, 1, 2, 3), q(w, planes), None, stride=2, padding=1)
+    report('conv-dgrad p%d' % planes, out, ref.permute(0, 2, 3, 4, 1).reshape(-1, cin), TOL_F32)
+    # ConvTranspose3d input gradient == MODE_CONV over dY with the transposed-conv weight
+    wt = rnd((cin, cout, 4, 4, 4), 3, 0.05)
+    dy2 = rnd((b, r, r, r, cout), 4)
+    rows = b * (r // 2) ** 3
+    out2 = torch.zeros((rows, cin), dtype=torch.float32, device='cuda')
+    raw.igemm(L.MODE_CONV, planes, raw.to_planes(dy2, planes), (b, r, r, r, cout), rows, 64 * cout,
+              raw.pack_convt_dgrad(wt, planes), cin, out2, cin, out_kind=L.OUT_F32)
+    ref2 = F.conv3d(q(dy2, planes).permute(0, 4, 1, 2, 3), q(wt, planes), None, stride=2, padding=1)
+    report('convt-dgrad p%d' % planes, out2, ref2.permute(0, 2, 3, 4, 1).reshape(rows, cin), TOL_F32)
+    check_error_word()
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+def test_patch_conv(planes):
+    L, raw = _imports()
+    b, r, cout = 3, 16, 64
+    vol = rnd((b, r, r, r), 1)
+    w = rnd((cout, 1, 4, 4, 4), 2, 0.2)
+    bias = rnd((cout,), 3)
+    rows = b * (r // 2) ** 3
+    out = torch.empty((rows, cout), dtype=torch.float32, device='cuda')
+    raw.igemm(L.MODE_PATCH, planes, vol, (b, r, r, r, 1), rows, 64, raw.pack_conv_fwd(w, planes), cout, out, cout,
+              out_kind=L.OUT_F32, bias=bias)
+    ref = F.conv3d(q(vol, planes).unsqueeze(1), q(w, planes), bias.double(), stride=2, padding=1)
+    report('patch p%d' % planes, out, ref.permute(0, 2, 3, 4, 1).reshape(rows, cout), TOL_F32)
+    check_error_word()
+
+
+@pytest.mark.parametrize('merge_n', [0, 1])
+@pytest.mark.parametrize('planes', [1, 2])
+def test_wgrad(planes, merge_n):
+    L, raw = _imports()
+    # dense: dW[out,in] = dY^T X
+    rows, cin, cout = 1000, 192, 256
+    x, dy = rnd((rows, cin), 1), rnd((rows, cout), 2)
+    g = torch.zeros((cout, cin), dtype=torch.float32, device='cuda')
+    raw.wgrad(L.MODE_DENSE, planes, raw.to_planes(dy, planes), cout, raw.to_planes(x, planes), (1, 1, 1, 1, cin), rows, g,
+              sm=cin, st=0, sc=1, m_valid=cout, merge_n=merge_n)
+    report('wgrad-dense p%d m%d' % (planes, merge_n), g, q(dy, planes).t() @ q(x, planes), TOL_F32)
+    # conv: dW[cout,cin,4,4,4]
+    for (b, r, cin, cout) in ((2, 8, 64, 128), (2, 8, 24, 48), (1, 8, 32, 200)):
+        x = rnd((b, r, r, r, cin), 3)
+        dy = rnd((b, r // 2, r // 2, r // 2, cout), 4)
+        rows = b * (r // 2) ** 3
+        g = torch.zeros((cout, cin, 4, 4, 4), dtype=torch.float32, device='cuda')
+        raw.wgrad(L.MODE_CONV, planes, raw.to_planes(dy, planes), cout, raw.to_planes(x, planes), (b, r, r, r, cin), rows, g,
+                  sm=cin * 64, st=1, sc=64, m_valid=cout, merge_n=merge_n)
+        xx = q(x, planes).permute(0, 4, 1, 2, 3).requires_grad_(False)
+        wref = torch.zeros((cout, cin, 4, 4, 4), dtype=torch.float64, device='cuda', requires_grad=True)
+        F.conv3d(xx, wref, None, stride=2, padding=1).backward(q(dy, planes).permute(0, 4, 1, 2, 3))
+        report('wgrad-conv p%d m%d %s' % (planes, merge_n, (b, r, cin, cout)), g, wref.grad, TOL_F32)
+    # patch: dW[cout,1,4,4,4]
+    b, r, cout = 2, 16, 64
+    vol = rnd((b, r, r, r), 5)
+    dy = rnd((b, r // 2, r // 2, r // 2, cout), 6)
+    rows = b * (r // 2) ** 3
+    g = torch.zeros((cout, 1, 4, 4, 4), dtype=torch.float32, device='cuda')
+    raw.wgrad(L.MODE_PATCH, planes, raw.to_planes(dy, planes), cout, vol, (b, r, r, r, 1), rows, g, sm=64, st=0, sc=1,
+              m_valid=cout, merge_n=merge_n)
+    wref = torch.zeros((cout, 1, 4, 4, 4), dtype=torch.float64, device='cuda', requires_grad=True)
+    F.conv3d(q(vol, planes).unsqueeze(1), wref, None, stride=2, padding=1).backward(q(dy, planes).permute(0, 4, 1, 2, 3))
+    report('wgrad-patch p%d m%d' % (planes, merge_n), g, wref.grad, TOL_F32)
+    check_error_word()
