@@ -61,8 +61,9 @@ typedef struct {
   int32_t n_pad, n_valid;
   int32_t bn, mt, ksplit; /* tile config: N tile (mult of 16, <=256), M sub-tiles per CTA (1|2), K splits; 0 = auto */
   const void* b_packed;   /* sg_pack_b image */
-  const float* bias;      /* [n_valid] or NULL */
+  const float* bias;      /* [n_valid] (or [bias_mod]) or NULL */
   int32_t act;
+  int32_t bias_mod;       /* >0: bias index = n % bias_mod (ConvTranspose3d on a 1^3 grid: n = pos*Cout + co) */
   const void* mask; /* optional bf16 planes, same layout as out: out *= act'(mask) with mask_act */
   int64_t mask_plane_stride;
   int32_t mask_act;
@@ -98,6 +99,7 @@ typedef struct {
   float* grad;
   int32_t accumulate; /* 1: += (torch .grad accumulation semantics) */
   float scale;
+  int32_t c_valid;    /* >0: only columns c < c_valid of each tap are emitted (zero-padded operands) */
 } sg_wgrad_reduce_args;
 int sg_wgrad_reduce(const sg_wgrad_reduce_args* a, void* stream);
 
@@ -115,6 +117,66 @@ typedef struct {
 } sg_pack_b_args;
 size_t sg_pack_b_bytes(const sg_pack_b_args* a);
 int sg_pack_b(const sg_pack_b_args* a, void* stream);
+
+/* ---- HBM-bound companions (all tensors are plane tensors viewed as [rows, C], C % 8 == 0) ----
+ * `*_ps` = plane stride in elements; `sums` = zero-initialised double workspace.                                  */
+
+/* g = ga * act'(y) (y = stored activation output); sums[0..c) += column sums of g (= bias gradient).
+ * replaces: LeakyReLU/ReLU backward + bias gradient reductions (model/gan.py:11..52, model/sdf_net.py:28..47)      */
+int sg_act_bwd(const void* ga, int64_t ga_ps, const void* y, int64_t y_ps, void* g, int64_t g_ps, int planes, int64_t rows,
+               int c, int act, double* sums, void* stream);
+/* train-mode BatchNorm3d/1d (model/gan.py:10,14,18; model/autoencoder.py:17..60): sums[0..c)=sum x, [c..2c)=sum x^2 */
+int sg_bn_stats(const void* x, int64_t x_ps, int planes, int64_t rows, int c, double* sums, void* stream);
+int sg_bn_finalize(const double* sums, int64_t rows, int c, float eps, float momentum, float* mean, float* invstd,
+                   float* running_mean, float* running_var, void* stream);
+int sg_bn_apply(const void* x, int64_t x_ps, void* y, int64_t y_ps, int planes, int64_t rows, int c, const float* mean,
+                const float* invstd, const float* gamma, const float* beta, int act, void* stream);
+int sg_bn_bwd_reduce(const void* ga, int64_t ga_ps, const void* y, int64_t y_ps, const void* x, int64_t x_ps, int planes,
+                     int64_t rows, int c, int act, const float* mean, const float* invstd, double* sums, void* stream);
+int sg_bn_bwd_apply(const void* ga, int64_t ga_ps, const void* y, int64_t y_ps, const void* x, int64_t x_ps, void* gx,
+                    int64_t gx_ps, int planes, int64_t rows, int c, int act, const float* mean, const float* invstd,
+                    const float* gamma, const double* sums, void* stream);
+/* dst[(i / wc)*s_t + (i % wc)*s_c] (+)= scale*src[i] */
+int sg_emit_sums(const double* src, float* dst, int n, int accumulate, float scale, int wc, int64_t s_t, int64_t s_c, void* stream);
+/* second stage of ConvTranspose3d(C->1,k4,s2,p1) (model/gan.py:21, model/autoencoder.py:63) and of the input
+ * gradient of Conv3d(1->C): out[n,2d,2h,2w] = act(bias + sum of the 8 taps of P[n*d*h*w, 64])                       */
+int sg_col2im_c1(const void* P, int64_t p_ps, int planes, int n, int d, int h, int w, const float* bias, int act, float* out,
+                 void* stream);
+int sg_unary_f32(const float* x, float* y, int64_t n, int act, void* stream);
+int sg_unary_bwd_f32(const float* gy, const float* y, float* gx, int64_t n, int act, void* stream);
+/* y[r] = act(x[r,:].w + b)  (Linear(256->1)+Tanh model/sdf_net.py:50-51; Conv3d(256->1,k4,s1) model/gan.py:55;
+ * Linear(128->1) model/progressive_gan.py:30) and its backward: gx = g*w, sums[0..c) += g*x, sums[c] += g            */
+/* weight element of column k lives at w[(k / wc)*s_t + (k % wc)*s_c] (wc % 8 == 0) */
+int sg_rowdot_fwd(const void* x, int64_t x_ps, int planes, int64_t rows, int c, const float* w, int wc, int64_t s_t, int64_t s_c,
+                  const float* bias, int act, float* y, void* stream);
+int sg_rowdot_bwd(const float* gy, const float* y, int act, const void* x, int64_t x_ps, int planes, int64_t rows, int c,
+                  const float* w, int wc, int64_t s_t, int64_t s_c, void* gx, int64_t gx_ps, double* sums, void* stream);
+int sg_to_planes(const float* src, int64_t src_ld, int64_t rows, int c_src, void* dst, int64_t dst_ps, int planes, int c_dst,
+                 void* stream);
+int sg_from_planes(const void* src, int64_t src_ps, int planes, int64_t rows, int c_src, int c_take, float* dst, int64_t dst_ld,
+                   int accumulate, float scale, void* stream);
+/* rows [x,y,z,latent,0..] of cat(points, latent_codes) (model/sdf_net.py:57); latent row i = index ? table[index[i]] : latent[i] */
+int sg_sdf_pack_input(const float* points, const float* latent, const int32_t* index, int L, int64_t n, void* dst, int64_t dst_ps,
+                      int planes, int c_dst, void* stream);
+int sg_sdf_unpack_grad(const void* ga, int64_t ga_ps, const void* gb, int64_t gb_ps, int planes, int64_t n, int c_src, int L,
+                       const int32_t* index, float* gpoints, float* glatent, void* stream);
+/* fade-in blend model/progressive_gan.py:48-50 */
+int sg_fade_fwd(const void* x, int64_t x_ps, void* y, int64_t y_ps, int planes, int b, int r, int c, const float* vol, float f,
+                void* stream);
+int sg_fade_bwd_vol(const void* g, int64_t g_ps, int planes, int b, int r, int c, float f, float* gvol, void* stream);
+int sg_axpby_planes(const void* a, int64_t a_ps, const void* b, int64_t b_ps, void* y, int64_t y_ps, int planes, int64_t elems,
+                    float alpha, float beta, void* stream);
+/* fused optimizer updates over flat fp32 arenas (torch.optim.RMSprop/Adam defaults: train_wgan.py:45-46,
+ * train_gan.py:28-31, train_sdf_autodecoder.py:44-45); clip>0 folds Discriminator.clip_weights (model/gan.py:67-69) */
+int sg_rmsprop(float* p, const float* g, float* sq, int64_t n, float lr, float alpha, float eps, float grad_scale, float clip,
+               void* stream);
+int sg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int step,
+            float grad_scale, void* stream);
+int sg_clamp(float* p, int64_t n, float lo, float hi, void* stream);
+/* loss_sum += mean|out-target| ; gout = sign(out-target)/n   (train_sdf_autodecoder.py:88 data term) */
+/* out[0] += sum x (double) */
+int sg_sum_f32(const float* x, int64_t n, double* out, void* stream);
+int sg_l1_loss_grad(const float* out, const float* target, float* gout, int64_t n, double* loss_sum, void* stream);
 
 /* ---- misc ---- */
 int sg_abi_version(void);

@@ -20,7 +20,7 @@ class SgIgemmArgs(ctypes.Structure):
     _fields_ = [('mode', c_int32), ('planes', c_int32), ('a', SgTensor), ('a2', SgTensor), ('rows', c_int64),
                 ('k', c_int32), ('n_pad', c_int32), ('n_valid', c_int32),
                 ('bn', c_int32), ('mt', c_int32), ('ksplit', c_int32),
-                ('b_packed', c_void_p), ('bias', c_void_p), ('act', c_int32),
+                ('b_packed', c_void_p), ('bias', c_void_p), ('act', c_int32), ('bias_mod', c_int32),
                 ('mask', c_void_p), ('mask_plane_stride', c_int64), ('mask_act', c_int32),
                 ('out', c_void_p), ('out_plane_stride', c_int64), ('out_kind', c_int32), ('out_ld', c_int32),
                 ('out_d', c_int32), ('out_h', c_int32), ('out_w', c_int32)]
@@ -34,7 +34,7 @@ class SgWgradArgs(ctypes.Structure):
 class SgWgradReduceArgs(ctypes.Structure):
     _fields_ = [('partials', c_void_p), ('ksplit', c_int32), ('m_pad', c_int32), ('m_valid', c_int32),
                 ('taps', c_int32), ('cb', c_int32), ('sm', c_int64), ('st', c_int64), ('sc', c_int64),
-                ('grad', c_void_p), ('accumulate', c_int32), ('scale', c_float)]
+                ('grad', c_void_p), ('accumulate', c_int32), ('scale', c_float), ('c_valid', c_int32)]
 
 
 class SgPackBArgs(ctypes.Structure):
@@ -58,7 +58,37 @@ SYMBOLS = {
     'sg_wgrad_reduce': (c_int32, [ctypes.POINTER(SgWgradReduceArgs), c_void_p]),
     'sg_pack_b_bytes': (c_size_t, [ctypes.POINTER(SgPackBArgs)]),
     'sg_pack_b': (c_int32, [ctypes.POINTER(SgPackBArgs), c_void_p]),
+    # p = pointer, l = int64, i = int32, f = float (see _sig)
+    'sg_act_bwd': 'plplpliliipp',
+    'sg_bn_stats': 'plilipp',
+    'sg_bn_finalize': 'pliffppppp',
+    'sg_bn_apply': 'plplilippppip',
+    'sg_bn_bwd_reduce': 'plplpliliipppp',
+    'sg_bn_bwd_apply': 'plplplpliliippppp',
+    'sg_emit_sums': 'ppiifillp',
+    'sg_col2im_c1': 'pliiiiipipp',
+    'sg_unary_f32': 'pplip',
+    'sg_unary_bwd_f32': 'ppplip',
+    'sg_rowdot_fwd': 'plilipillpipp',
+    'sg_rowdot_bwd': 'ppiplilipillplpp',
+    'sg_to_planes': 'pllipliip',
+    'sg_from_planes': 'pliliiplifp',
+    'sg_sdf_pack_input': 'pppilpliip',
+    'sg_sdf_unpack_grad': 'plpliliipppp',
+    'sg_fade_fwd': 'plpliiiipfp',
+    'sg_fade_bwd_vol': 'pliiiifpp',
+    'sg_axpby_planes': 'plplplilffp',
+    'sg_rmsprop': 'ppplfffffp',
+    'sg_adam': 'pppplffffifp',
+    'sg_clamp': 'plffp',
+    'sg_sum_f32': 'plpp',
+    'sg_l1_loss_grad': 'ppplpp',
 }
+
+_SIG = {'p': c_void_p, 'l': c_int64, 'i': c_int32, 'f': c_float}
+for _k, _v in list(SYMBOLS.items()):
+    if isinstance(_v, str):
+        SYMBOLS[_k] = (c_int32, [_SIG[ch] for ch in _v])
 
 _lib = None
 

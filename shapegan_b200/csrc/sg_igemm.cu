@@ -28,7 +28,7 @@ struct IgemmP {
   const char* a2_ptr; long long a2_ps; int a2C;
   long long rows; int kchunks, n_pad, n_valid, bn, mt, ksplit, classes;
   const char* b;
-  const float* bias; int act;
+  const float* bias; int act, bias_mod;
   const bf16* mask; long long mask_ps; int mask_act;
   char* out; long long out_ps; int out_kind, out_ld, oD, oH, oW;
   int stages, m_tiles, n_tiles; long long work_total;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
               long long off = 0; uint32_t nbytes = 0;
               if (ri_n[sub][i] >= 0) {
                 if (p.mode == SG_MODE_DENSE) {
-                  off = (long long)ri_n[sub][i] * rowC + coff; nbytes = 16;
+                  if (coff < rowC) { off = (long long)ri_n[sub][i] * rowC + coff; nbytes = 16; }
                 } else {
                   const uint32_t c = ri_c[sub][i];
                   const int d = (int)(c & 1023) - 1 + dd, h = (int)((c >> 10) & 1023) - 1 + dh, x = (int)((c >> 20) & 1023) - 1 + dw;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float x = __uint_as_float(r[j8 + j]);
-              if (add_bias && n + j < p.n_valid) x += __ldg(p.bias + n + j);
+              if (add_bias && n + j < p.n_valid) x += __ldg(p.bias + (p.bias_mod > 0 ? (n + j) % p.bias_mod : n + j));
               v[j] = apply_act(x, p.act);
             }
             const long long eoff = orow * p.out_ld + n;
@@ -399,9 +399,10 @@ static int igemm_validate(const sg_igemm_args* a) {
   if (a->rows < 0) return sg_fail(-6, "sg_igemm: negative rows");
   if (!a->a.ptr || !a->b_packed || !a->out) return sg_fail(-7, "sg_igemm: null tensor");
   if (a->mode == SG_MODE_DENSE) {
-    int kk = a->a.c + (a->a2.ptr ? a->a2.c : 0);
-    if (kk != a->k) return sg_fail(-8, "sg_igemm: DENSE needs K == a.c (+ a2.c)");
-    if (a->a2.ptr && ((a->a.c & 63) || (a->a2.c & 63))) return sg_fail(-9, "sg_igemm: two-source DENSE needs 64-multiples");
+    if (a->a.c & 7) return sg_fail(-8, "sg_igemm: DENSE needs C % 8 == 0");
+    int kk = a->a2.ptr ? a->a.c + ((a->a2.c + 63) & ~63) : ((a->a.c + 63) & ~63);
+    if (kk != a->k) return sg_fail(-8, "sg_igemm: DENSE needs K == roundup64(a.c) (or a.c + roundup64(a2.c))");
+    if (a->a2.ptr && ((a->a.c & 63) || (a->a2.c & 7))) return sg_fail(-9, "sg_igemm: two-source DENSE needs a.c % 64 == 0, a2.c % 8 == 0");
   } else if (a->mode == SG_MODE_CONV) {
     if ((a->a.c & 7) || a->k != 64 * a->a.c) return sg_fail(-10, "sg_igemm: CONV needs C%8==0 and K==64*C");
     if ((a->a.d | a->a.h | a->a.w) & 1) return sg_fail(-11, "sg_igemm: CONV needs even dims");
@@ -433,7 +434,7 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   p.a2_ptr = (const char*)a->a2.ptr; p.a2_ps = a->a2.plane_stride; p.a2C = a->a2.c;
   p.rows = a->rows; p.kchunks = a->k / 64; p.n_pad = a->n_pad; p.n_valid = a->n_valid;
   p.classes = (a->mode == SG_MODE_CONVT) ? 8 : 1;
-  p.b = (const char*)a->b_packed; p.bias = a->bias; p.act = a->act;
+  p.b = (const char*)a->b_packed; p.bias = a->bias; p.act = a->act; p.bias_mod = a->bias_mod;
   p.mask = (const bf16*)a->mask; p.mask_ps = a->mask_plane_stride; p.mask_act = a->mask_act;
   p.out = (char*)a->out; p.out_ps = a->out_plane_stride; p.out_kind = a->out_kind; p.out_ld = a->out_ld;
   p.oD = a->out_d; p.oH = a->out_h; p.oW = a->out_w;
@@ -462,6 +463,12 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   {  // no empty split
     int cps = (p.kchunks + ksplit - 1) / ksplit;
     ksplit = (p.kchunks + cps - 1) / cps;
+  }
+  // explicit/auto mt=2 that would leave fewer than 2 pipeline stages falls back to one M sub-tile
+  if (mt == 2) {
+    unsigned sb = ((unsigned)(2 * a->planes * kTileBytes + a->planes * bn * 128) + 1023u) & ~1023u;
+    unsigned kt = (a->mode == SG_MODE_CONV || a->mode == SG_MODE_CONVT) ? (unsigned)((p.kchunks * 8 * 4 + 1023) & ~1023) : 0u;
+    if ((227u * 1024u - kSmemHeader - kt) / sb < 2) mt = 1;
   }
   p.bn = bn; p.mt = mt; p.ksplit = ksplit;
   p.n_tiles = n_tiles;

@@ -273,6 +273,7 @@ __global__ void sg_wgrad_reduce_kernel(const sg_wgrad_reduce_args a) {
     const int m = (int)(i / n_total);
     const int n = (int)(i - (long long)m * n_total);
     const int tap = n / a.cb, c = n - tap * a.cb;
+    if (a.c_valid > 0 && c >= a.c_valid) continue;
     float acc = 0.f;
     for (int s = 0; s < a.ksplit; ++s) acc += a.partials[((size_t)s * a.m_pad + m) * n_total + n];
     float* g = a.grad + (long long)m * a.sm + (long long)tap * a.st + (long long)c * a.sc;

@@ -49,7 +49,7 @@ def null_tensor():
 def pack_b(w, planes, n_valid, k_pad, taps, c_count, c_valid, s_n0, s_tap, s_c, classes=1, n0_count=None, s_n1=0,
            n_pad=None):
     _require_cuda(w)
-    assert w.dtype == torch.float32 and w.is_contiguous()
+    assert w.dtype == torch.float32      # may be a strided view: all addressing goes through the explicit strides
     n_pad = round_up(n_valid, 16) if n_pad is None else n_pad
     a = L.SgPackBArgs(ctypes.c_void_p(w.data_ptr()), None, planes, classes, n_pad, n_valid,
                       n0_count if n0_count is not None else n_pad, s_n1, s_n0, k_pad, taps, c_count, c_valid, s_tap, s_c)
@@ -99,7 +99,7 @@ def pack_linear_dgrad(w, planes, n_pad=None):
 
 # ------------------------------------------------------------------------------------------------- implicit GEMM
 def igemm(mode, planes, a, a_dims, rows, k, b_img, n_valid, out, out_ld, out_kind=L.OUT_BF16, bias=None, act=L.ACT_NONE,
-          a2=None, a2_c=0, mask=None, mask_act=L.ACT_NONE, out_dims=(0, 0, 0), bn=0, mt=0, ksplit=0, n_pad=None):
+          a2=None, a2_c=0, mask=None, mask_act=L.ACT_NONE, out_dims=(0, 0, 0), bn=0, mt=0, ksplit=0, n_pad=None, bias_mod=0):
     _require_cuda(a, b_img, out)
     n_pad = round_up(n_valid, 16) if n_pad is None else n_pad
     n, d, h, w, c = a_dims
@@ -112,6 +112,7 @@ def igemm(mode, planes, a, a_dims, rows, k, b_img, n_valid, out, out_ld, out_kin
     args.b_packed = ctypes.c_void_p(b_img.data_ptr())
     args.bias = ctypes.c_void_p(bias.data_ptr()) if bias is not None else None
     args.act = act
+    args.bias_mod = bias_mod
     if mask is not None:
         args.mask = ctypes.c_void_p(mask.data_ptr())
         args.mask_plane_stride = mask.stride(0) if mask.shape[0] == 2 else 0
@@ -125,7 +126,7 @@ def igemm(mode, planes, a, a_dims, rows, k, b_img, n_valid, out, out_ld, out_kin
 
 
 def wgrad(b_mode, planes, a, a_c, b, b_dims, rows, grad, sm, st, sc, m_valid, cb=None, taps=None, accumulate=False,
-          scale=1.0, merge_n=1, ksplit=0):
+          scale=1.0, merge_n=1, ksplit=0, c_valid=0):
     """grad[m*sm + tap*st + c*sc] (+)= sum_rows A[row,m] * gather(B)[row(+tap), c]."""
     _require_cuda(a, b, grad)
     n, d, h, w, c = b_dims
@@ -147,7 +148,7 @@ def wgrad(b_mode, planes, a, a_c, b, b_dims, rows, grad, sm, st, sc, m_valid, cb
     if taps is not None:
         taps_r, cb_r = taps, cb
     r = L.SgWgradReduceArgs(ctypes.c_void_p(ws.data_ptr()), args.ksplit_out, round_up(a_c, 128), m_valid, taps_r, cb_r,
-                            sm, st, sc, ctypes.c_void_p(grad.data_ptr()), 1 if accumulate else 0, scale)
+                            sm, st, sc, ctypes.c_void_p(grad.data_ptr()), 1 if accumulate else 0, scale, c_valid)
     L.check(L.lib().sg_wgrad_reduce(ctypes.byref(r), stream()), 'sg_wgrad_reduce')
     return grad
 
@@ -156,3 +157,178 @@ def device_error_word():
     p = ctypes.c_void_p()
     L.check(L.lib().sg_device_error_word(ctypes.byref(p)), 'sg_device_error_word')
     return p.value
+
+
+# ------------------------------------------------------------------------------------------------- HBM-bound companions
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _ps(t):
+    return t.stride(0) if (t is not None and t.shape[0] == 2) else 0
+
+
+def _call(name, *args):
+    L.check(getattr(L.lib(), name)(*args, stream()), name)
+
+
+def dsums(n, device):
+    return torch.zeros(n, dtype=torch.float64, device=device)
+
+
+def act_bwd(ga, y, act, c, want_sums=False, want_g=True):
+    """g = ga * act'(y) over plane tensors viewed as [rows, c]; optional column sums (bias gradient)."""
+    planes = ga.shape[0]
+    rows = ga[0].numel() // c
+    g = torch.empty_like(ga) if want_g else None
+    sums = dsums(2 * c, ga.device) if want_sums else None
+    _call('sg_act_bwd', _p(ga), _ps(ga), _p(y), _ps(y) if y is not None else 0, _p(g), _ps(g), planes, rows, c, act, _p(sums))
+    return g, sums
+
+
+def emit_sums(sums, dst, n, accumulate=False, scale=1.0, wc=0, s_t=0, s_c=1):
+    _call('sg_emit_sums', _p(sums), _p(dst), n, 1 if accumulate else 0, scale, wc, s_t, s_c)
+    return dst
+
+
+def bn_forward(x, c, gamma, beta, act, running_mean, running_var, eps, momentum, training):
+    """train: batch statistics (+ running-stat update); eval: running statistics.  Returns y, mean, invstd."""
+    planes = x.shape[0]
+    rows = x[0].numel() // c
+    dev = x.device
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    if training:
+        sums = dsums(2 * c, dev)
+        _call('sg_bn_stats', _p(x), _ps(x), planes, rows, c, _p(sums))
+        _call('sg_bn_finalize', _p(sums), rows, c, eps, momentum, _p(mean), _p(invstd), _p(running_mean), _p(running_var))
+    else:
+        # eval-mode statistics are tiny [C] vectors prepared with torch scalar math
+        mean.copy_(running_mean)
+        invstd.copy_(torch.rsqrt(running_var + eps))
+    y = torch.empty_like(x)
+    _call('sg_bn_apply', _p(x), _ps(x), _p(y), _ps(y), planes, rows, c, _p(mean), _p(invstd), _p(gamma), _p(beta), act)
+    return y, mean, invstd
+
+
+def bn_backward(ga, y, x, c, act, mean, invstd, gamma):
+    """returns gx (planes), ggamma, gbeta (fp32 [c])"""
+    planes = x.shape[0]
+    rows = x[0].numel() // c
+    sums = dsums(2 * c, x.device)
+    _call('sg_bn_bwd_reduce', _p(ga), _ps(ga), _p(y), _ps(y), _p(x), _ps(x), planes, rows, c, act, _p(mean), _p(invstd), _p(sums))
+    gx = torch.empty_like(x)
+    _call('sg_bn_bwd_apply', _p(ga), _ps(ga), _p(y), _ps(y), _p(x), _ps(x), _p(gx), _ps(gx), planes, rows, c, act, _p(mean),
+          _p(invstd), _p(gamma), _p(sums))
+    gbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    ggamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    emit_sums(sums, gbeta, c)
+    emit_sums(sums[c:], ggamma, c)
+    return gx, ggamma, gbeta
+
+
+def col2im_c1(pm, n, d, h, w, bias, act):
+    out = torch.empty((n, 2 * d, 2 * h, 2 * w), dtype=torch.float32, device=pm.device)
+    _call('sg_col2im_c1', _p(pm), _ps(pm), pm.shape[0], n, d, h, w, _p(bias), act, _p(out))
+    return out
+
+
+def unary_f32(x, act):
+    y = torch.empty_like(x)
+    _call('sg_unary_f32', _p(x), _p(y), x.numel(), act)
+    return y
+
+
+def unary_bwd_f32(gy, y, act):
+    gx = torch.empty_like(y)
+    _call('sg_unary_bwd_f32', _p(gy.contiguous()), _p(y), _p(gx), y.numel(), act)
+    return gx
+
+
+def rowdot_fwd(x, c, w, bias, act, wc=0, s_t=0, s_c=1):
+    rows = x[0].numel() // c
+    y = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _call('sg_rowdot_fwd', _p(x), _ps(x), x.shape[0], rows, c, _p(w), wc, s_t, s_c, _p(bias), act, _p(y))
+    return y
+
+
+def rowdot_bwd(gy, y, act, x, c, w, need_gx, need_gw, planes, rows, wc=0, s_t=0, s_c=1):
+    dev = gy.device
+    gx = torch.empty((planes, rows, c), dtype=torch.bfloat16, device=dev) if need_gx else None
+    sums = dsums(c + 8, dev) if need_gw else None
+    _call('sg_rowdot_bwd', _p(gy), _p(y), act, _p(x) if need_gw else None, _ps(x) if x is not None else 0, planes, rows, c, _p(w),
+          wc, s_t, s_c, _p(gx), _ps(gx), _p(sums))
+    return gx, sums
+
+
+def f32_to_planes(src, planes, c_dst=None):
+    """fp32 [rows, c_src] (row stride = src.stride(0)) -> planes [P, rows, c_dst] (zero padded)."""
+    rows, c_src = src.shape
+    c_dst = round_up(c_src, 8) if c_dst is None else c_dst
+    assert src.stride(1) == 1
+    dst = torch.empty((planes, rows, c_dst), dtype=torch.bfloat16, device=src.device)
+    _call('sg_to_planes', _p(src), src.stride(0), rows, c_src, _p(dst), _ps(dst), planes, c_dst)
+    return dst
+
+
+def planes_to_f32(src, c_src, c_take=None, out=None, accumulate=False, scale=1.0):
+    rows = src[0].numel() // c_src
+    c_take = c_src if c_take is None else c_take
+    if out is None:
+        out = torch.empty((rows, c_take), dtype=torch.float32, device=src.device)
+    _call('sg_from_planes', _p(src), _ps(src), src.shape[0], rows, c_src, c_take, _p(out), out.stride(0), 1 if accumulate else 0, scale)
+    return out
+
+
+def sdf_pack_input(points, latent, index, L_, planes, c_dst):
+    n = points.shape[0]
+    dst = torch.empty((planes, n, c_dst), dtype=torch.bfloat16, device=points.device)
+    _call('sg_sdf_pack_input', _p(points), _p(latent), _p(index), L_, n, _p(dst), _ps(dst), planes, c_dst)
+    return dst
+
+
+def sdf_unpack_grad(ga, gb, c_src, L_, index, gpoints, glatent):
+    n = ga.shape[1]
+    _call('sg_sdf_unpack_grad', _p(ga), _ps(ga), _p(gb), _ps(gb), ga.shape[0], n, c_src, L_, _p(index), _p(gpoints), _p(glatent))
+
+
+def fade_fwd(x, b, r, c, vol, f):
+    y = torch.empty_like(x)
+    _call('sg_fade_fwd', _p(x), _ps(x), _p(y), _ps(y), x.shape[0], b, r, c, _p(vol), f)
+    return y
+
+
+def fade_bwd_vol(g, b, r, c, f, gvol):
+    _call('sg_fade_bwd_vol', _p(g), _ps(g), g.shape[0], b, r, c, f, _p(gvol))
+    return gvol
+
+
+def axpby_planes(a, alpha, b=None, beta=0.0):
+    y = torch.empty_like(a)
+    _call('sg_axpby_planes', _p(a), _ps(a), _p(b), _ps(b), _p(y), _ps(y), a.shape[0], a[0].numel(), alpha, beta)
+    return y
+
+
+def rmsprop(p, g, sq, lr, alpha=0.99, eps=1e-8, grad_scale=1.0, clip=0.0):
+    _call('sg_rmsprop', _p(p), _p(g), _p(sq), p.numel(), lr, alpha, eps, grad_scale, clip)
+
+
+def adam(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+    _call('sg_adam', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale)
+
+
+def clamp_(p, lo, hi):
+    _call('sg_clamp', _p(p), p.numel(), lo, hi)
+
+
+def l1_loss_grad(out, target, want_grad=True):
+    gout = torch.empty_like(out) if want_grad else None
+    loss = dsums(1, out.device)
+    _call('sg_l1_loss_grad', _p(out), _p(target), _p(gout), out.numel(), _p(loss))
+    return loss, gout
+
+
+def sum_f32(x):
+    out = dsums(1, x.device)
+    _call('sg_sum_f32', _p(x), x.numel(), _p(out))
+    return out

@@ -1,0 +1,155 @@
+"""DeepSDF MLP (model/sdf_net.py:23-61) as one autograd Function over libsg_b200.
+
+forward : cat(points, latent) -> 4x(Linear+ReLU) -> cat(x, input) -> 3x(Linear+ReLU) -> Linear -> tanh
+Layer-by-layer variant: every Linear is one tcgen05 implicit-GEMM launch with the bias+ReLU epilogue fused; the
+skip concat (sdf_net.py:59) is never materialised (two-source K loop); the 256->1 head + tanh is a row-dot kernel.
+The backward is hand scheduled (no autograd graph between layers): act-bwd+bias-sum, wgrad, dgrad per layer.
+`fused=True` swaps the forward for the persistent fused kernel (sg_sdfnet.cu) when available."""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib as L
+from . import config, raw
+from .ops import PACK_CACHE, r64
+
+HID = 256          # SDF_NET_BREADTH, model/sdf_net.py:21
+
+
+def _pack_lin(w, planes, c_valid, k_pad):
+    return raw.pack_b(w, planes, w.shape[0], k_pad, 1, k_pad, c_valid, s_n0=w.stride(0), s_tap=0, s_c=1)
+
+
+def _pack_lin_t(w, planes, n_valid, n_pad, col0=0):
+    """B[n = in-feature (col0 + n), k = out-feature] = W[k, col0 + n]"""
+    out_f = w.shape[0]
+    view = w[:, col0:]
+    return raw.pack_b(view, planes, n_valid, r64(out_f), 1, r64(out_f), out_f, s_n0=1, s_tap=0, s_c=w.stride(0), n_pad=n_pad)
+
+
+class SDFNetFunction(Function):
+    """args: points [N,3] fp32, latent fp32 ([N,L] rows, or a [S,L] table when `index` int32 [N] is given),
+    then the 16 parameters in state_dict order (layers1.{0,2,4,6}.{weight,bias}, layers2.{0,2,4,6}.{weight,bias})."""
+
+    @staticmethod
+    def forward(ctx, points, latent, index, *params):
+        planes = config.planes()
+        n = points.shape[0]
+        dev = points.device
+        lat = latent.shape[1]
+        cin = 3 + lat
+        cin8 = r64(cin)            # input rows are physically zero-padded to a 64-multiple (K chunks, wgrad atoms)
+        w = [params[2 * i] for i in range(8)]
+        b = [params[2 * i + 1] for i in range(8)]
+        points = points.contiguous()
+        latent = latent.contiguous()
+        x_in = raw.sdf_pack_input(points, latent, index, lat, planes, cin8)
+        hs = []
+        h = x_in
+        for i in range(4):                                   # layers1 (sdf_net.py:26-38)
+            kin = cin8 if i == 0 else HID
+            img = PACK_CACHE.get(w[i], 'sdf_f%d' % i, planes, lambda t, pl, i=i, kin=kin: _pack_lin(
+                t, pl, cin if i == 0 else HID, r64(kin)))
+            y = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
+            raw.igemm(L.MODE_DENSE, planes, h, (1, 1, 1, 1, kin), n, r64(kin), img, HID, y, HID, bias=b[i], act=L.ACT_RELU)
+            hs.append(y)
+            h = y
+        # layers2.0 on cat(x, input) (sdf_net.py:59, :41): two-source K loop, K = 256 + roundup64(cin8)
+        k5 = HID + r64(cin8)
+        img = PACK_CACHE.get(w[4], 'sdf_f4', planes, lambda t, pl: _pack_lin(t, pl, HID + cin, k5))
+        y = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
+        raw.igemm(L.MODE_DENSE, planes, h, (1, 1, 1, 1, HID), n, k5, img, HID, y, HID, bias=b[4], act=L.ACT_RELU,
+                  a2=x_in, a2_c=cin8)
+        hs.append(y)
+        h = y
+        for i in (5, 6):
+            img = PACK_CACHE.get(w[i], 'sdf_f%d' % i, planes, lambda t, pl: _pack_lin(t, pl, HID, HID))
+            y = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
+            raw.igemm(L.MODE_DENSE, planes, h, (1, 1, 1, 1, HID), n, HID, img, HID, y, HID, bias=b[i], act=L.ACT_RELU)
+            hs.append(y)
+            h = y
+        out = raw.rowdot_fwd(h, HID, w[7], b[7], L.ACT_TANH)                  # sdf_net.py:50-51
+        ctx.meta = (planes, n, lat, cin, cin8, index is not None, latent.shape[0])
+        ctx.save_for_backward(x_in, out, index if index is not None else torch.empty(0, device=dev), *hs, *w)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        planes, n, lat, cin, cin8, indexed, lat_rows = ctx.meta
+        saved = ctx.saved_tensors
+        x_in, out, index = saved[0], saved[1], saved[2]
+        hs = list(saved[3:10])
+        w = list(saved[10:18])
+        dev = gout.device
+        need_points = ctx.needs_input_grad[0]
+        need_latent = ctx.needs_input_grad[1]
+        need_w = [ctx.needs_input_grad[3 + 2 * i] for i in range(8)]
+        need_b = [ctx.needs_input_grad[4 + 2 * i] for i in range(8)]
+        gw = [None] * 8
+        gb = [None] * 8
+        gout = gout.contiguous()
+
+        def f32(shape):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+
+        # ---- head: Linear(256->1) + tanh
+        gh, sums = raw.rowdot_bwd(gout, out, L.ACT_TANH, hs[6], HID, w[7], True, need_w[7] or need_b[7], planes, n)
+        if need_w[7] or need_b[7]:
+            gw[7] = raw.emit_sums(sums, f32(w[7].shape), HID)
+            gb[7] = raw.emit_sums(sums[HID:], f32((1,)), 1)
+        gx_a = gx_b = None
+        for i in (6, 5, 4, 3, 2, 1, 0):
+            g, sums = raw.act_bwd(gh, hs[i], L.ACT_RELU, HID, want_sums=need_b[i])
+            if need_b[i]:
+                gb[i] = raw.emit_sums(sums, f32((HID,)), HID)
+            src = hs[i - 1] if i > 0 else x_in
+            if i == 4:
+                # W5 = [hidden 256 | xyz 3 | latent L]  (sdf_net.py:59)
+                if need_w[4]:
+                    gw[4] = f32(w[4].shape)
+                    raw.wgrad(L.MODE_DENSE, planes, g, HID, hs[3], (1, 1, 1, 1, HID), n, gw[4], sm=HID + cin, st=0, sc=1, m_valid=HID)
+                    _wgrad_input(planes, g, x_in, cin, cin8, n, gw[4][:, HID:], HID + cin)
+                if need_points or need_latent:
+                    img = PACK_CACHE.get(w[4], 'sdf_t4in', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8, col0=HID))
+                    gx_b = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
+                    raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, cin, gx_b, cin8, n_pad=raw.round_up(cin8, 16))
+                img = PACK_CACHE.get(w[4], 'sdf_t4h', planes, lambda t, pl: _pack_lin_t(t, pl, HID, HID))
+                gh = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
+                raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, HID, gh, HID)
+            elif i == 0:
+                if need_w[0]:
+                    gw[0] = f32(w[0].shape)
+                    _wgrad_input(planes, g, x_in, cin, cin8, n, gw[0], cin)
+                if need_points or need_latent:
+                    img = PACK_CACHE.get(w[0], 'sdf_t0', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8))
+                    gx_a = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
+                    raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, cin, gx_a, cin8, n_pad=raw.round_up(cin8, 16))
+            else:
+                if need_w[i]:
+                    gw[i] = f32(w[i].shape)
+                    raw.wgrad(L.MODE_DENSE, planes, g, HID, src, (1, 1, 1, 1, HID), n, gw[i], sm=HID, st=0, sc=1, m_valid=HID)
+                img = PACK_CACHE.get(w[i], 'sdf_t%d' % i, planes, lambda t, pl: _pack_lin_t(t, pl, HID, HID))
+                gh = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
+                raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, HID, gh, HID)
+        gpoints = glatent = None
+        if need_points or need_latent:
+            gpoints = f32((n, 3)) if need_points else None
+            if need_latent:
+                glatent = torch.zeros((lat_rows, lat), dtype=torch.float32, device=dev) if indexed else f32((n, lat))
+            raw.sdf_unpack_grad(gx_a, gx_b, cin8, lat, index if indexed else None, gpoints, glatent)
+        grads = [gpoints, glatent, None]
+        for i in range(8):
+            grads.append(gw[i])
+            grads.append(gb[i])
+        return tuple(grads)
+
+
+def _wgrad_input(planes, g, x_in, cin, cin8, n, grad_view, ld):
+    """dW[:, input columns] = g^T x_in  where x_in has cin8 (multiple of 8) physical columns, cin valid.
+    sg_wgrad needs a column count that is a multiple of 64; the reduce only emits the valid columns."""
+    raw.wgrad(L.MODE_DENSE, planes, g, HID, x_in, (1, 1, 1, 1, cin8), n, grad_view, sm=ld, st=0, sc=1, m_valid=HID, c_valid=cin)
+
+
+def sdfnet_apply(points, latent, index, params):
+    return SDFNetFunction.apply(points, latent, index, *params)

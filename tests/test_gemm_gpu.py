@@ -9,6 +9,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 TOL_F32 = 2e-5
+TOL_F32X = 1e-4     # hi/lo bf16 split drops the lo*lo term (2^-18) and the tensor core truncates long fp32 sums
 TOL_BF16 = 6e-3
 
 
@@ -64,7 +65,7 @@ def test_dense(planes, rows, k, n, bn, mt):
     out = torch.empty((rows, n), dtype=torch.float32, device='cuda')
     raw.igemm(L.MODE_DENSE, planes, xp, (1, 1, 1, 1, k), rows, k, img, n, out, n, out_kind=L.OUT_F32, bias=bias, bn=bn, mt=mt)
     ref = q(x, planes) @ q(w, planes).t() + bias.double()
-    report('dense p%d %s' % (planes, (rows, k, n)), out, ref, TOL_F32)
+    report('dense p%d %s' % (planes, (rows, k, n)), out, ref, TOL_F32 if planes == 1 else TOL_F32X)
     # bf16 plane output + activation
     outp = torch.empty((planes, rows, n), dtype=torch.bfloat16, device='cuda')
     raw.igemm(L.MODE_DENSE, planes, xp, (1, 1, 1, 1, k), rows, k, img, n, outp, n, bias=bias, act=L.ACT_LRELU, bn=bn, mt=mt)
@@ -148,7 +149,7 @@ def test_conv_dgrad_and_convt_dgrad(planes):
     raw.igemm(L.MODE_CONV, planes, raw.to_planes(dy2, planes), (b, r, r, r, cout), rows, 64 * cout,
               raw.pack_convt_dgrad(wt, planes), cin, out2, cin, out_kind=L.OUT_F32)
     ref2 = F.conv3d(q(dy2, planes).permute(0, 4, 1, 2, 3), q(wt, planes), None, stride=2, padding=1)
-    report('convt-dgrad p%d' % planes, out2, ref2.permute(0, 2, 3, 4, 1).reshape(rows, cin), TOL_F32)
+    report('convt-dgrad p%d' % planes, out2, ref2.permute(0, 2, 3, 4, 1).reshape(rows, cin), TOL_F32 if planes == 1 else TOL_F32X)
     check_error_word()
 
 
