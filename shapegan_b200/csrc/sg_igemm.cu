@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
           const char* src_base; long long src_ps; int rowC, coff;
           int dd = 0, dh = 0, dw = 0;
           if (p.mode == SG_MODE_DENSE) {
-            const int c1chunks = p.aC >> 6;
+            const int c1chunks = (p.aC + 63) >> 6;      // chunks served by the first source (its tail chunk is zero-filled)
             if (kc < c1chunks) { src_base = p.a_ptr; src_ps = p.a_ps; rowC = p.aC; coff = kc * 64 + g * 8; }
             else { src_base = p.a2_ptr; src_ps = p.a2_ps; rowC = p.a2C; coff = (kc - c1chunks) * 64 + g * 8; }
           } else {

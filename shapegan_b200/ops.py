@@ -13,6 +13,8 @@ with the LeakyReLU masks held fixed.
 
 Tensors between layers are NDHWC bf16 plane tensors [P, B, D, H, W, C] (P = 1 bf16, P = 2 hi/lo fp32x);
 single-channel voxel volumes at module boundaries are fp32 [B, D, H, W]."""
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -26,21 +28,41 @@ r64 = lambda v: raw.round_up(v, 64)   # noqa: E731
 
 # ------------------------------------------------------------------------------------------------- packed-weight cache
 class _PackCache:
-    """fp32 parameter -> tensor-core operand image.  Keyed by (storage, version, kind, planes); an optimizer step or
-    load_state_dict bumps `_version`.  `.data` mutations do not: call invalidate() (our clip_weights does)."""
+    """fp32 parameter -> tensor-core operand image, cached per parameter OBJECT (a uid stamped on the tensor; a
+    device address can be recycled by the caching allocator, so it is not an identity) and validated by
+    (`_version`, data_ptr, shape).  An optimizer step or load_state_dict bumps `_version`; `.data` mutations do not:
+    call invalidate() (our clip_weights does).  Entries die with their parameter (weakref.finalize)."""
 
     def __init__(self):
         self.store = {}
+        self.next_uid = 1
+
+    def _uid(self, w):
+        uid = getattr(w, '_sg_uid', None)
+        if uid is None:
+            uid = self.next_uid
+            self.next_uid += 1
+            try:
+                w._sg_uid = uid
+                weakref.finalize(w, self._drop, uid)
+            except Exception:               # un-stampable tensor: never cached
+                return None
+        return uid
+
+    def _drop(self, uid):
+        for key in [k for k in self.store if k[0] == uid]:
+            self.store.pop(key, None)
 
     def get(self, w, kind, planes, fn):
-        key = (w.data_ptr(), kind, planes)
-        hit = self.store.get(key)
-        ver = w._version
-        if hit is not None and hit[0] == ver and hit[2] == tuple(w.shape):
+        uid = self._uid(w)
+        key = (uid, kind, planes)
+        sig = (w._version, w.data_ptr(), tuple(w.shape))
+        hit = self.store.get(key) if uid is not None else None
+        if hit is not None and hit[0] == sig:
             return hit[1]
         img = fn(w.detach(), planes)
-        if not torch.cuda.is_current_stream_capturing():
-            self.store[key] = (ver, img, tuple(w.shape))
+        if uid is not None and not torch.cuda.is_current_stream_capturing():
+            self.store[key] = (sig, img)
         return img
 
     def invalidate(self):
@@ -309,12 +331,14 @@ class _Fwd(Function):
         x = x.contiguous()
         y = op.fwd(x, w, bias, act)
         ctx.op, ctx.act, ctx.has_bias = op, act, bias is not None
+        ctx.w_obj = w                       # identity for the pack cache; saved_tensors still does the version check
         ctx.save_for_backward(x, w, y)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w, y = ctx.saved_tensors
+        x, _w_checked, y = ctx.saved_tensors
+        w = ctx.w_obj
         op = ctx.op
         gy = gy.contiguous()
         c = op.out_channels()
@@ -335,12 +359,14 @@ class _Tr(Function):
     def forward(ctx, op, g, w):
         g = g.contiguous()
         ctx.op = op
+        ctx.w_obj = w
         ctx.save_for_backward(g, w)
         return op.tr(g, w)
 
     @staticmethod
     def backward(ctx, ggx):
-        g, w = ctx.saved_tensors
+        g, _w_checked = ctx.saved_tensors
+        w = ctx.w_obj
         op = ctx.op
         ggx = ggx.contiguous()
         g_g = _Fwd.apply(op, ggx, w, None, ACT_NONE) if ctx.needs_input_grad[1] else None
@@ -528,13 +554,15 @@ class _ConvT1Act(Function):
         x = x.contiguous()
         y = op.fwd(x, w, bias.detach() if bias is not None else None, act)
         ctx.op, ctx.act, ctx.has_bias = op, act, bias is not None
+        ctx.w_obj = w
         ctx.save_for_backward(x, w, y)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x, w, y = ctx.saved_tensors
+        x, _w_checked, y = ctx.saved_tensors
+        w = ctx.w_obj
         op = ctx.op
         g = raw.unary_bwd_f32(gy.contiguous(), y, ctx.act) if ctx.act != ACT_NONE else gy.contiguous()
         gx = op.tr(g, w) if ctx.needs_input_grad[1] else None

@@ -70,6 +70,7 @@ class SDFNetFunction(Function):
             h = y
         out = raw.rowdot_fwd(h, HID, w[7], b[7], L.ACT_TANH)                  # sdf_net.py:50-51
         ctx.meta = (planes, n, lat, cin, cin8, index is not None, latent.shape[0])
+        ctx.w_objs = w                       # parameter identities for the pack cache
         ctx.save_for_backward(x_in, out, index if index is not None else torch.empty(0, device=dev), *hs, *w)
         return out
 
@@ -80,7 +81,7 @@ class SDFNetFunction(Function):
         saved = ctx.saved_tensors
         x_in, out, index = saved[0], saved[1], saved[2]
         hs = list(saved[3:10])
-        w = list(saved[10:18])
+        w = ctx.w_objs                       # saved[10:18] were version-checked by autograd
         dev = gout.device
         need_points = ctx.needs_input_grad[0]
         need_latent = ctx.needs_input_grad[1]
