@@ -1,0 +1,188 @@
+"""Training-step bodies of the reference's scripts on the B200-native modules, with the optimizer and the
+data-parallel gradient exchange fused the B200 way:
+
+  * all parameters of a module live in ONE flat fp32 arena, all gradients in another (autograd accumulates straight
+    into views of it), so a step is: backward -> ONE NCCL all-reduce of the flat gradient arena over NVLink (only
+    when world_size > 1) -> ONE fused RMSprop/Adam kernel (sg_rmsprop / sg_adam) that also applies 1/world_size and,
+    for the critic, the weight clip of model/gan.py:67-69.
+  * batches shard over samples: every rank owns `batch` samples (weak scaling); there is no other exchange.
+    BatchNorm statistics are per replica (like nn.DataParallel in the reference, train_hybrid_progressive_gan.py:62-68).
+
+Step definitions:
+  WGANStep            train_wgan.py:62-71 (critic update, clip) + :75-84 (generator update); `gp=True` adds the gradient
+                      penalty of train_hybrid_progressive_gan.py:102-111 to the critic loss instead of clipping (D1).
+  GANStep             train_gan.py:58-86 (G step, D-fake step, D-real step; Adam 1e-3 / 1e-5).
+  AutodecoderStep     train_sdf_autodecoder.py:77-91 with `//` at :78 (two Adams, lr 1e-5, L1 + 0.01*mean(z^2)).
+  VAEStep             train_autoencoder.py:98-117 (Adam 5e-5).
+"""
+import torch
+import torch.distributed as dist
+
+from . import raw
+
+
+class FlatOptimizer:
+    """Flat-arena RMSprop / Adam with torch.optim default hyper-parameters (train_wgan.py:45-46, train_gan.py:28-31)."""
+
+    def __init__(self, params, kind, lr, clip=0.0, world_size=1):
+        self.params = [p for p in params]
+        seen, uniq = set(), []
+        for p in self.params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        self.kind, self.lr, self.clip, self.world = kind, lr, clip, world_size
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p.data)           # parameters become views of the arena
+            p.grad = self.grad[off:off + k].view_as(p.data)           # autograd accumulates in place into the arena
+            off += k
+        self.s1 = torch.zeros(n, dtype=torch.float32, device=dev)     # square_avg / exp_avg
+        self.s2 = torch.zeros(n, dtype=torch.float32, device=dev) if kind == 'adam' else None
+        self.steps = 0
+        from .ops import invalidate_weight_cache
+        invalidate_weight_cache()
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self):
+        if self.world > 1:
+            dist.all_reduce(self.grad)                                 # NCCL ring/NVLS over NVLink 5
+        self.steps += 1
+        scale = 1.0 / self.world
+        if self.kind == 'rmsprop':
+            raw.rmsprop(self.flat, self.grad, self.s1, self.lr, grad_scale=scale, clip=self.clip)
+        else:
+            raw.adam(self.flat, self.grad, self.s1, self.s2, self.lr, self.steps, grad_scale=scale)
+        _bump_versions(self.params)
+
+
+def _bump_versions(params):
+    """The fused kernels write parameter memory behind autograd's back: bump the version counters (host-only) so the
+    packed-weight cache and autograd's saved-tensor checks see the mutation."""
+    try:
+        for p in params:
+            torch.autograd.graph.increment_version(p)
+    except Exception:
+        from .ops import invalidate_weight_cache
+        invalidate_weight_cache()
+
+
+def gradient_penalty(critic, real, fake, alpha, weight=10.0):
+    """train_hybrid_progressive_gan.py:102-111 with alpha [B,1,1,1] injected (device RNG in the reference)."""
+    a = alpha.expand(real.shape)
+    xi = (a * real + (1 - a) * fake).detach().requires_grad_(True)
+    out = critic(xi)
+    grads = torch.autograd.grad(outputs=out, inputs=xi, grad_outputs=torch.ones_like(out), create_graph=True,
+                                retain_graph=True, only_inputs=True)[0]
+    return ((grads.norm(2, dim=(1, 2, 3)) - 1) ** 2).mean() * weight
+
+
+class WGANStep:
+    def __init__(self, generator, critic, lr=0.00005, clip=0.01, gp=False, gp_weight=10.0, world_size=1):
+        self.gen, self.cri, self.gp, self.gp_weight = generator, critic, gp, gp_weight
+        critic.use_sigmoid = False                                     # train_wgan.py:31
+        self.gopt = FlatOptimizer(generator.parameters(), 'rmsprop', lr, world_size=world_size)
+        self.copt = FlatOptimizer(critic.parameters(), 'rmsprop', lr, clip=0.0 if gp else clip, world_size=world_size)
+
+    def __call__(self, real, z_critic, z_gen, alpha=None):
+        """real [B,32,32,32] fp32, z_* [B,128] fp32, alpha [B,1,1,1] (GP variant) — all on the device.
+        Returns (critic_loss, generator_loss) as 0-d device tensors (no host sync)."""
+        gen, cri = self.gen, self.cri
+        self.gopt.zero_grad(); self.copt.zero_grad()                    # train_wgan.py:62-63
+        with torch.no_grad():
+            fake = gen(z_critic)                                       # .detach() at :65: no graph is needed
+        closs = torch.mean(cri(fake)) - torch.mean(cri(real))          # :66-68
+        if self.gp:
+            closs = closs + gradient_penalty(cri, real, fake.squeeze(1), alpha, self.gp_weight)
+        closs.backward()                                               # :69
+        self.copt.step()                                               # :70-71 (clip fused)
+        self.gopt.zero_grad(); self.copt.zero_grad()                    # :75-76
+        gloss = -torch.mean(cri(gen(z_gen)))                           # :78-82
+        gloss.backward()                                               # :83
+        self.gopt.step()                                               # :84
+        return closs.detach(), gloss.detach()
+
+
+class GANStep:
+    """train_gan.py:58-86."""
+
+    def __init__(self, generator, discriminator, world_size=1):
+        self.gen, self.dis = generator, discriminator
+        self.gopt = FlatOptimizer(generator.parameters(), 'adam', 0.001, world_size=world_size)
+        self.dopt = FlatOptimizer(discriminator.parameters(), 'adam', 0.00001, world_size=world_size)
+
+    def __call__(self, real, z_gen, z_dis):
+        bce = torch.nn.functional.binary_cross_entropy
+        gen, dis = self.gen, self.dis
+        b = real.shape[0]
+        self.gopt.zero_grad(); self.dopt.zero_grad()
+        gloss = -torch.mean(torch.log(dis(gen(z_gen))))                # :61-65
+        gloss.backward()
+        self.gopt.step()
+        self.dopt.zero_grad()
+        with torch.no_grad():
+            fake = gen(z_dis)
+        out_fake = dis(fake)
+        floss = bce(out_fake, torch.zeros(b, device=real.device))      # :76-79
+        floss.backward()
+        self.dopt.step()
+        self.dopt.zero_grad()
+        vloss = bce(dis(real), torch.ones(b, device=real.device))      # :82-85
+        vloss.backward()
+        self.dopt.step()
+        return gloss.detach(), floss.detach(), vloss.detach()
+
+
+class AutodecoderStep:
+    """train_sdf_autodecoder.py:77-91: the latent table is a raw leaf tensor with its own Adam."""
+
+    def __init__(self, sdf_net, latent_table, lr=1e-5, sigma=0.01, world_size=1):
+        self.net, self.sigma = sdf_net, sigma
+        self.table = latent_table.detach().clone().requires_grad_(True)
+        self.nopt = FlatOptimizer(sdf_net.parameters(), 'adam', lr, world_size=world_size)
+        self.lopt = FlatOptimizer([self.table], 'adam', lr, world_size=world_size)
+
+    def __call__(self, points, sdf, shape_index):
+        """points [N,3], sdf [N], shape_index int32 [N] (= point_index // POINTCLOUD_SIZE, :78 with the D6 fix)."""
+        self.nopt.zero_grad(); self.lopt.zero_grad()                    # :84-86
+        out = self.net(points, self.table, shape_index)                # :80,87 without materialising table[index]
+        # mean(z_batch^2) over the gathered rows == sum_s count_s*|table_s|^2 / (N*L): [S,L] math instead of [N,L]
+        counts = torch.bincount(shape_index, minlength=self.table.shape[0]).to(torch.float32)
+        reg = (counts.unsqueeze(1) * torch.pow(self.table, 2)).sum() / (points.shape[0] * self.table.shape[1])
+        loss = torch.mean(torch.abs(out - sdf)) + self.sigma * reg     # :88
+        loss.backward()                                                # :89
+        self.nopt.step(); self.lopt.step()                              # :90-91
+        return loss.detach()
+
+
+class VAEStep:
+    """train_autoencoder.py:98-117."""
+
+    def __init__(self, autoencoder, world_size=1):
+        self.m = autoencoder
+        self.opt = FlatOptimizer(autoencoder.parameters(), 'adam', 0.00005, world_size=world_size)
+
+    def __call__(self, batch):
+        m = self.m
+        self.opt.zero_grad()
+        m.train()
+        if m.is_variational:
+            out, mean, logvar = m(batch)
+            kld = -0.5 * torch.sum(1 + logvar - mean.pow(2) - logvar.exp()) / mean.nelement()      # :54-55
+        else:
+            out, kld = m(batch), 0
+        diff = out - batch
+        diff = torch.where(batch < 0, diff * 32, diff)                  # :57-62
+        loss = torch.mean(torch.abs(diff)) + kld
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
