@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     // ================================================================ PRODUCERS
     const int g = tid & 7, rb = tid >> 3;
     int s = 0; uint32_t ph = 0;
-    int prev_s = -1;
+    // loads run `lag` stages ahead of the completion signal: keeps (lag+1) x stage bytes in flight per SM
+    const int lag = max(1, S - 2);
+    int pending = 0, oldest = 0;
     const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
       int cls, nt, mtile, ks;
@@ -228,12 +230,19 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
           }
         }
         cp_async_commit();
-        if (prev_s >= 0) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&hdr->full[prev_s]); }
-        prev_s = s;
+        if (++pending > lag) {
+          cp_async_wait_dyn(lag); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+          if (++oldest == S) oldest = 0;
+          --pending;
+        }
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-    if (prev_s >= 0) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&hdr->full[prev_s]); }
+    while (pending > 0) {
+      cp_async_wait_dyn(pending - 1); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+      if (++oldest == S) oldest = 0;
+      --pending;
+    }
   } else if (warp == 4) {
     // ================================================================ MMA ISSUER
     const uint32_t idesc = umma_idesc(128, p.bn, false, false);

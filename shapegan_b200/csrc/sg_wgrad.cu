@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
   if (warp < 4) {
     // ================================================================ PRODUCERS
     const int g = tid & 7, rb = tid >> 3;
-    int s = 0; uint32_t ph = 0; int prev_s = -1;
+    int s = 0; uint32_t ph = 0;
+    const int lag = max(1, S - 2);
+    int pending = 0, oldest = 0;
     const int oW = p.bW >> 1, oH = p.bH >> 1, oD = p.bD >> 1;   // CONV/PATCH: rows enumerate the stride-2 output grid
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
       const int ks = (int)(w % p.ksplit);
@@ -164,12 +166,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
           }
         }
         cp_async_commit();
-        if (prev_s >= 0) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&hdr->full[prev_s]); }
-        prev_s = s;
+        if (++pending > lag) {
+          cp_async_wait_dyn(lag); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+          if (++oldest == S) oldest = 0;
+          --pending;
+        }
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-    if (prev_s >= 0) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&hdr->full[prev_s]); }
+    while (pending > 0) {
+      cp_async_wait_dyn(pending - 1); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+      if (++oldest == S) oldest = 0;
+      --pending;
+    }
   } else if (warp == 4) {
     // ================================================================ MMA ISSUER
     int s = 0; uint32_t ph = 0; int it = 0;
