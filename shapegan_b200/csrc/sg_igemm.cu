@@ -12,8 +12,11 @@
 #include <algorithm>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "sg_common.cuh"
 #include "sg_internal.h"
+#include "sg_tma.h"
 
 namespace sg {
 
@@ -35,6 +38,10 @@ struct IgemmP {
   int acc_bufs, acc_slot;
   unsigned ktab_bytes, stage_bytes, a_stage_bytes;
   int* err;
+  // TMA gather (C % 64 == 0, power-of-two grids): a tile of 128 rows is the box (bx,by,bz,bn) of the row grid (gx,gy,gz)
+  int use_tma, bx, by, bz, bnn, gx, gy, gz;
+  CUtensorMap tmA[2];    // per plane
+  CUtensorMap tmA2[2];   // second DENSE source
 };
 
 struct SmemHeader {
@@ -62,7 +69,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], kProducerThreads + 1); mbar_init(&hdr->empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], p.use_tma ? 1 : kProducerThreads + 1); mbar_init(&hdr->empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128); }
     fence_mbar_init();
   }
@@ -89,8 +96,61 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
 
   const int cps = (p.kchunks + p.ksplit - 1) / p.ksplit;   // K chunks per split
 
-  if (warp < 4) {
-    // ================================================================ PRODUCERS
+  if (warp < 4 && p.use_tma) {
+    // ================================================================ TMA PRODUCER (one thread)
+    if (tid == 0) {
+      tma_prefetch_desc(&p.tmA[0]);
+      if (p.planes == 2) tma_prefetch_desc(&p.tmA[1]);
+      int s = 0; uint32_t ph = 0;
+      const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+      const uint32_t tx_bytes = p.a_stage_bytes + b_tile_bytes * p.planes;
+      const int c1chunks = (p.aC + 63) >> 6;
+      for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+        int cls, nt, mtile, ks;
+        decode_work(p, w, cls, nt, mtile, ks);
+        const int pd = (cls >> 2) & 1, phh = (cls >> 1) & 1, pw = cls & 1;
+        const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
+        for (int kc = k0; kc < k1; ++kc) {
+          mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+          uint64_t* bar = &hdr->full[s];
+          const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
+          mbar_arrive_expect_tx(bar, tx_bytes);
+          int c0 = 0, ox = 0, oy = 0, oz = 0, mul = 1;
+          if (p.mode != SG_MODE_DENSE) {
+            const int k = kc * 64, tap = k / p.aC;
+            c0 = k - tap * p.aC;
+            if (p.mode == SG_MODE_CONV) { oz = (tap >> 4) - 1; oy = ((tap >> 2) & 3) - 1; ox = (tap & 3) - 1; mul = 2; }
+            else {
+              const int td = (tap >> 2) & 1, th = (tap >> 1) & 1, tw = tap & 1;
+              oz = pd ? 1 - td : -td; oy = phh ? 1 - th : -th; ox = pw ? 1 - tw : -tw;
+            }
+          }
+          for (int sub = 0; sub < p.mt; ++sub) {
+            const long long row0 = ((long long)mtile * p.mt + sub) * kTileRows;
+            for (int pl = 0; pl < p.planes; ++pl) {
+              const uint32_t dst = a_base + (uint32_t)(sub * p.planes + pl) * kTileBytes;
+              if (p.mode == SG_MODE_DENSE) {
+                if (kc < c1chunks) tma_load_2d(dst, &p.tmA[pl], kc * 64, (int)row0, bar);
+                else tma_load_2d(dst, &p.tmA2[pl], (kc - c1chunks) * 64, (int)row0, bar);
+              } else {
+                const int x0 = (int)(row0 % p.gx); long long t = row0 / p.gx;
+                const int y0 = (int)(t % p.gy); t /= p.gy;
+                const int z0 = (int)(t % p.gz); const int n0 = (int)(t / p.gz);
+                tma_load_5d(dst, &p.tmA[pl], c0, mul * x0 + ox, mul * y0 + oy, mul * z0 + oz, n0, bar);
+              }
+            }
+          }
+          const uint32_t b_dst = a_base + p.a_stage_bytes;
+          for (int pl = 0; pl < p.planes; ++pl) {
+            const char* src = p.b + ((((size_t)cls * p.kchunks + kc) * p.planes + pl) * p.n_pad + (size_t)nt * p.bn) * 128;
+            bulk_g2s(b_dst + pl * b_tile_bytes, src, b_tile_bytes, bar);
+          }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================================================ PRODUCERS (cp.async gather fallback)
     const int g = tid & 7, rb = tid >> 3;
     int s = 0; uint32_t ph = 0;
     // loads run `lag` stages ahead of the completion signal: keeps (lag+1) x stage bytes in flight per SM
@@ -494,6 +554,47 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return sg_fail(-23, "sg_igemm: tile does not fit shared memory");
   p.stages = stages;
+  // ---- TMA gather: the whole A tile of a (tap, 64-channel) chunk is one tensor-map box
+  p.use_tma = 0;
+  {
+    const char* no_tma = getenv("SG_B200_NO_TMA");
+    const bool want = !(no_tma && no_tma[0] == '1') && a->mode != SG_MODE_PATCH && (a->a.c % 64) == 0 &&
+                      (!a->a2.ptr || (a->a2.c % 64) == 0) && ((uintptr_t)a->a.ptr % 16) == 0 && a->rows < (1LL << 31);
+    if (want) {
+      bool ok = true;
+      const uint32_t one[5] = {1, 1, 1, 1, 1};
+      if (a->mode == SG_MODE_DENSE) {
+        const uint32_t box[2] = {64, 128};
+        for (int pl = 0; pl < a->planes && ok; ++pl) {
+          uint64_t dims[2] = {(uint64_t)a->a.c, (uint64_t)a->rows};
+          uint64_t str[1] = {(uint64_t)a->a.c * 2};
+          ok = tma_make_map(&p.tmA[pl], (const char*)a->a.ptr + (size_t)pl * a->a.plane_stride * 2, 2, dims, str, box, one);
+          if (ok && a->a2.ptr) {
+            uint64_t dims2[2] = {(uint64_t)a->a2.c, (uint64_t)a->rows};
+            uint64_t str2[1] = {(uint64_t)a->a2.c * 2};
+            ok = tma_make_map(&p.tmA2[pl], (const char*)a->a2.ptr + (size_t)pl * a->a2.plane_stride * 2, 2, dims2, str2, box, one);
+          }
+        }
+      } else {
+        const bool conv = a->mode == SG_MODE_CONV;
+        const int gx = conv ? a->a.w / 2 : a->a.w, gy = conv ? a->a.h / 2 : a->a.h, gz = conv ? a->a.d / 2 : a->a.d;
+        TileBox tb;
+        ok = tile_box(kTileRows, gx, gy, gz, &tb) && a->rows == (long long)a->a.n * gx * gy * gz;
+        if (ok) {
+          const uint64_t C = (uint64_t)a->a.c, W = (uint64_t)a->a.w, H = (uint64_t)a->a.h, D = (uint64_t)a->a.d;
+          uint64_t dims[5] = {C, W, H, D, (uint64_t)a->a.n};
+          uint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, D * H * W * C * 2};
+          const uint32_t m = conv ? 2u : 1u;
+          uint32_t box[5] = {64, m * tb.bx, m * tb.by, m * tb.bz, (uint32_t)tb.bn};
+          uint32_t es[5] = {1, m, m, m, 1};
+          for (int pl = 0; pl < a->planes && ok; ++pl)
+            ok = tma_make_map(&p.tmA[pl], (const char*)a->a.ptr + (size_t)pl * a->a.plane_stride * 2, 5, dims, str, box, es);
+          p.gx = gx; p.gy = gy; p.gz = gz; p.bx = tb.bx; p.by = tb.by; p.bz = tb.bz; p.bnn = tb.bn;
+        }
+      }
+      p.use_tma = ok ? 1 : 0;
+    }
+  }
   const size_t smem = kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {

@@ -6,8 +6,11 @@
 #include <algorithm>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "sg_common.cuh"
 #include "sg_internal.h"
+#include "sg_tma.h"
 
 namespace sg {
 
@@ -27,6 +30,8 @@ struct WgradP {
   int stages; unsigned stage_bytes, tile_bytes;
   long long work_total;
   int* err;
+  int use_tma, gx, gy, gz;
+  CUtensorMap tmA[2], tmB[2];
 };
 
 struct WgHeader {
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], 128); mbar_init(&hdr->empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], p.use_tma ? 1 : 128); mbar_init(&hdr->empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128); }
     fence_mbar_init();
   }
@@ -60,8 +65,51 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
   const int tps = (p.row_tiles + p.ksplit - 1) / p.ksplit;    // row tiles (stages) per split
   const int rpi = p.rs / 16;                                   // rows handled per producer thread per atom
 
-  if (warp < 4) {
-    // ================================================================ PRODUCERS
+  if (warp < 4 && p.use_tma) {
+    // ================================================================ TMA PRODUCER (one thread): every atom is one box
+    if (tid == 0) {
+      tma_prefetch_desc(&p.tmA[0]);
+      tma_prefetch_desc(&p.tmB[0]);
+      int s = 0; uint32_t ph = 0;
+      for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+        const int ks = (int)(w % p.ksplit);
+        const int ng = (int)((w / p.ksplit) % p.n_groups);
+        const int mtile = (int)(w / ((long long)p.ksplit * p.n_groups));
+        const int m0 = mtile * 128;
+        const int nb_atoms = min(kAtomsB, (p.n_total - ng * 256) / 64);
+        const uint32_t tx_bytes = (uint32_t)((kAtomsA + nb_atoms) * p.planes) * p.tile_bytes;
+        const int t0 = ks * tps, t1 = min(p.row_tiles, t0 + tps);
+        for (int rt = t0; rt < t1; ++rt) {
+          mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+          uint64_t* bar = &hdr->full[s];
+          const uint32_t base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
+          mbar_arrive_expect_tx(bar, tx_bytes);
+          const long long row0 = (long long)rt * p.rs;
+          for (int at = 0; at < kAtomsA; ++at)
+            for (int pl = 0; pl < p.planes; ++pl)
+              tma_load_2d(base + (uint32_t)(at * p.planes + pl) * p.tile_bytes, &p.tmA[pl], m0 + at * 64, (int)row0, bar);
+          const uint32_t bbase = base + (uint32_t)(kAtomsA * p.planes) * p.tile_bytes;
+          int x0 = 0, y0 = 0, z0 = 0, n0 = 0;
+          if (p.b_mode == SG_MODE_CONV) {
+            x0 = (int)(row0 % p.gx); long long t = row0 / p.gx;
+            y0 = (int)(t % p.gy); t /= p.gy;
+            z0 = (int)(t % p.gz); n0 = (int)(t / p.gz);
+          }
+          for (int j = 0; j < nb_atoms; ++j) {
+            const int n = ng * 256 + j * 64;
+            const int tap = n / p.Cb, cb = n - tap * p.Cb;
+            for (int pl = 0; pl < p.planes; ++pl) {
+              const uint32_t dst = bbase + (uint32_t)(j * p.planes + pl) * p.tile_bytes;
+              if (p.b_mode == SG_MODE_DENSE) tma_load_2d(dst, &p.tmB[pl], cb, (int)row0, bar);
+              else tma_load_5d(dst, &p.tmB[pl], cb, 2 * x0 - 1 + (tap & 3), 2 * y0 - 1 + ((tap >> 2) & 3), 2 * z0 - 1 + (tap >> 4), n0, bar);
+            }
+          }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================================================ PRODUCERS (cp.async gather fallback)
     const int g = tid & 7, rb = tid >> 3;
     int s = 0; uint32_t ph = 0;
     const int lag = max(1, S - 2);
@@ -363,6 +411,41 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
   p.partials = a->partials;
   p.work_total = (long long)p.m_tiles * p.n_groups * p.ksplit;
   p.err = sg_error_word();
+  p.use_tma = 0;
+  {
+    const char* no_tma = getenv("SG_B200_NO_TMA");
+    const bool want = !(no_tma && no_tma[0] == '1') && a->b_mode != SG_MODE_PATCH && (p.Ca % 64) == 0 && (p.Cb % 64) == 0 &&
+                      ((uintptr_t)a->a.ptr % 16) == 0 && ((uintptr_t)a->b.ptr % 16) == 0 && a->rows < (1LL << 31);
+    if (want) {
+      bool ok = true;
+      const uint32_t one[5] = {1, 1, 1, 1, 1};
+      const uint32_t box2[2] = {64, (uint32_t)p.rs};
+      TileBox tb = {0, 0, 0, 0};
+      if (a->b_mode == SG_MODE_CONV) {
+        p.gx = a->b.w / 2; p.gy = a->b.h / 2; p.gz = a->b.d / 2;
+        ok = tile_box(p.rs, p.gx, p.gy, p.gz, &tb) && a->rows == (long long)a->b.n * p.gx * p.gy * p.gz;
+      }
+      for (int pl = 0; pl < a->planes && ok; ++pl) {
+        uint64_t dA[2] = {(uint64_t)p.Ca, (uint64_t)a->rows};
+        uint64_t sA[1] = {(uint64_t)p.Ca * 2};
+        ok = tma_make_map(&p.tmA[pl], p.a_ptr + (size_t)pl * p.a_ps * 2, 2, dA, sA, box2, one);
+        if (!ok) break;
+        if (a->b_mode == SG_MODE_DENSE) {
+          uint64_t dB[2] = {(uint64_t)p.Cb, (uint64_t)a->rows};
+          uint64_t sB[1] = {(uint64_t)p.Cb * 2};
+          ok = tma_make_map(&p.tmB[pl], p.b_ptr + (size_t)pl * p.b_ps * 2, 2, dB, sB, box2, one);
+        } else {
+          const uint64_t C = (uint64_t)p.Cb, W = (uint64_t)a->b.w, H = (uint64_t)a->b.h, D = (uint64_t)a->b.d;
+          uint64_t dB[5] = {C, W, H, D, (uint64_t)a->b.n};
+          uint64_t sB[4] = {C * 2, W * C * 2, H * W * C * 2, D * H * W * C * 2};
+          uint32_t box[5] = {64, 2u * tb.bx, 2u * tb.by, 2u * tb.bz, (uint32_t)tb.bn};
+          uint32_t es[5] = {1, 2, 2, 2, 1};
+          ok = tma_make_map(&p.tmB[pl], p.b_ptr + (size_t)pl * p.b_ps * 2, 5, dB, sB, box, es);
+        }
+      }
+      p.use_tma = ok ? 1 : 0;
+    }
+  }
   const size_t smem = kWgHeader + (size_t)p.stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
