@@ -229,6 +229,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32x'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ad-shapes', type=int, default=512, help='autodecoder workload: number of shapes (16384 points each)')
     args = ap.parse_args()
     if args.impl == 'reference':
         rank = int(os.environ.get('RANK', '0'))
@@ -354,7 +355,7 @@ def bench_autodecoder(args, rank, world, dev, lib):
     from model.sdf_net import SDFNet
     from shapegan_b200 import train
     torch.manual_seed(0)
-    shapes, per = 512, 16384
+    shapes, per = args.ad_shapes, 16384
     n = shapes * per
     net = SDFNet()
     g = torch.Generator().manual_seed(5 + rank)

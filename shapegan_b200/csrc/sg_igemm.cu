@@ -52,11 +52,11 @@ struct SmemHeader {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void decode_work(const IgemmP& p, long long w, int& cls, int& nt, int& mtile, int& ks) {
-  ks = (int)(w % p.ksplit); w /= p.ksplit;
-  mtile = (int)(w % p.m_tiles); w /= p.m_tiles;
-  nt = (int)(w % p.n_tiles);
-  cls = (int)(w / p.n_tiles);
+__device__ __forceinline__ void decode_work(const IgemmP& p, long long w64, int& cls, int& nt, int& mtile, int& ks) {
+  uint32_t w = (uint32_t)w64;              // work_total < 2^31 (checked on the host): 32-bit division only
+  if (p.ksplit > 1) { ks = (int)(w % (uint32_t)p.ksplit); w /= (uint32_t)p.ksplit; } else ks = 0;
+  mtile = (int)(w % (uint32_t)p.m_tiles); w /= (uint32_t)p.m_tiles;
+  if (p.n_tiles > 1) { nt = (int)(w % (uint32_t)p.n_tiles); cls = (int)(w / (uint32_t)p.n_tiles); } else { nt = 0; cls = (int)w; }
 }
 
 __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid_constant__ IgemmP p) {
@@ -105,46 +105,54 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
       const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
       const uint32_t tx_bytes = p.a_stage_bytes + b_tile_bytes * p.planes;
       const int c1chunks = (p.aC + 63) >> 6;
+      // power-of-two row grid: tile origin by shifts/masks, once per tile (no 64-bit division in the K loop)
+      const int lgx = 31 - __clz(max(p.gx, 1)), lgy = 31 - __clz(max(p.gy, 1)), lgz = 31 - __clz(max(p.gz, 1));
       for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
         int cls, nt, mtile, ks;
         decode_work(p, w, cls, nt, mtile, ks);
         const int pd = (cls >> 2) & 1, phh = (cls >> 1) & 1, pw = cls & 1;
         const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
+        const int mul = (p.mode == SG_MODE_CONV) ? 2 : 1;
+        int tx0[2], ty0[2], tz0[2], tn0[2], trow[2];
+        for (int sub = 0; sub < p.mt; ++sub) {
+          const uint32_t row0 = (uint32_t)((mtile * p.mt + sub) * kTileRows);
+          trow[sub] = (int)row0;
+          tx0[sub] = mul * (int)(row0 & (uint32_t)(p.gx - 1));
+          ty0[sub] = mul * (int)((row0 >> lgx) & (uint32_t)(p.gy - 1));
+          tz0[sub] = mul * (int)((row0 >> (lgx + lgy)) & (uint32_t)(p.gz - 1));
+          tn0[sub] = (int)(row0 >> (lgx + lgy + lgz));
+        }
+        int tap = 0, c0 = 0;
+        if (p.mode != SG_MODE_DENSE) { tap = (k0 * 64) / p.aC; c0 = k0 * 64 - tap * p.aC; }
+        const char* bsrc = p.b + (((size_t)cls * p.kchunks + k0) * p.planes * p.n_pad + (size_t)nt * p.bn) * 128;
+        const size_t bplane = (size_t)p.n_pad * 128;
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
           uint64_t* bar = &hdr->full[s];
           const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
           mbar_arrive_expect_tx(bar, tx_bytes);
-          int c0 = 0, ox = 0, oy = 0, oz = 0, mul = 1;
-          if (p.mode != SG_MODE_DENSE) {
-            const int k = kc * 64, tap = k / p.aC;
-            c0 = k - tap * p.aC;
-            if (p.mode == SG_MODE_CONV) { oz = (tap >> 4) - 1; oy = ((tap >> 2) & 3) - 1; ox = (tap & 3) - 1; mul = 2; }
-            else {
-              const int td = (tap >> 2) & 1, th = (tap >> 1) & 1, tw = tap & 1;
-              oz = pd ? 1 - td : -td; oy = phh ? 1 - th : -th; ox = pw ? 1 - tw : -tw;
-            }
+          int ox = 0, oy = 0, oz = 0;
+          if (p.mode == SG_MODE_CONV) { oz = (tap >> 4) - 1; oy = ((tap >> 2) & 3) - 1; ox = (tap & 3) - 1; }
+          else if (p.mode == SG_MODE_CONVT) {
+            const int td = (tap >> 2) & 1, th = (tap >> 1) & 1, tw = tap & 1;
+            oz = pd ? 1 - td : -td; oy = phh ? 1 - th : -th; ox = pw ? 1 - tw : -tw;
           }
           for (int sub = 0; sub < p.mt; ++sub) {
-            const long long row0 = ((long long)mtile * p.mt + sub) * kTileRows;
             for (int pl = 0; pl < p.planes; ++pl) {
               const uint32_t dst = a_base + (uint32_t)(sub * p.planes + pl) * kTileBytes;
               if (p.mode == SG_MODE_DENSE) {
-                if (kc < c1chunks) tma_load_2d(dst, &p.tmA[pl], kc * 64, (int)row0, bar);
-                else tma_load_2d(dst, &p.tmA2[pl], (kc - c1chunks) * 64, (int)row0, bar);
+                if (kc < c1chunks) tma_load_2d(dst, &p.tmA[pl], kc * 64, trow[sub], bar);
+                else tma_load_2d(dst, &p.tmA2[pl], (kc - c1chunks) * 64, trow[sub], bar);
               } else {
-                const int x0 = (int)(row0 % p.gx); long long t = row0 / p.gx;
-                const int y0 = (int)(t % p.gy); t /= p.gy;
-                const int z0 = (int)(t % p.gz); const int n0 = (int)(t / p.gz);
-                tma_load_5d(dst, &p.tmA[pl], c0, mul * x0 + ox, mul * y0 + oy, mul * z0 + oz, n0, bar);
+                tma_load_5d(dst, &p.tmA[pl], c0, tx0[sub] + ox, ty0[sub] + oy, tz0[sub] + oz, tn0[sub], bar);
               }
             }
           }
           const uint32_t b_dst = a_base + p.a_stage_bytes;
-          for (int pl = 0; pl < p.planes; ++pl) {
-            const char* src = p.b + ((((size_t)cls * p.kchunks + kc) * p.planes + pl) * p.n_pad + (size_t)nt * p.bn) * 128;
-            bulk_g2s(b_dst + pl * b_tile_bytes, src, b_tile_bytes, bar);
-          }
+          for (int pl = 0; pl < p.planes; ++pl) bulk_g2s(b_dst + pl * b_tile_bytes, bsrc + pl * bplane, b_tile_bytes, bar);
+          bsrc += (size_t)p.planes * bplane;
+          c0 += 64;
+          if (c0 >= p.aC) { c0 = 0; ++tap; }
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
@@ -524,7 +532,8 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   }
   if (bn > 256 || (bn & 15) || a->n_pad % bn) return sg_fail(-20, "sg_igemm: bad bn");
   const int n_tiles = a->n_pad / bn;
-  if (mt <= 0) mt = (row_tiles * p.classes * n_tiles >= 2LL * sms && bn * 2 <= 512) ? 2 : 1;
+  // two M sub-tiles share every B tile (halves the weight traffic out of L2) once there is more than one wave of work
+  if (mt <= 0) mt = (row_tiles * p.classes * n_tiles > sms && bn * 2 <= 512) ? 2 : 1;
   if (mt < 1 || mt > 2 || mt * bn > 512) return sg_fail(-21, "sg_igemm: bad mt");
   if (ksplit <= 0) ksplit = 1;
   if (ksplit > p.kchunks) ksplit = p.kchunks;
@@ -543,6 +552,7 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   p.n_tiles = n_tiles;
   p.m_tiles = (int)((row_tiles + mt - 1) / mt);
   p.work_total = (long long)p.classes * n_tiles * p.m_tiles * ksplit;
+  if (p.work_total >= (1LL << 31)) return sg_fail(-24, "sg_igemm: too many tiles");
   p.acc_slot = (bn + 31) & ~31;
   p.acc_bufs = (2 * mt * p.acc_slot <= 512) ? 2 : 1;
   p.a_stage_bytes = (unsigned)(mt * a->planes * kTileBytes);

@@ -71,37 +71,44 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
       tma_prefetch_desc(&p.tmA[0]);
       tma_prefetch_desc(&p.tmB[0]);
       int s = 0; uint32_t ph = 0;
+      const int lgx = 31 - __clz(max(p.gx, 1)), lgy = 31 - __clz(max(p.gy, 1)), lgz = 31 - __clz(max(p.gz, 1));
       for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
-        const int ks = (int)(w % p.ksplit);
-        const int ng = (int)((w / p.ksplit) % p.n_groups);
-        const int mtile = (int)(w / ((long long)p.ksplit * p.n_groups));
+        const uint32_t w32 = (uint32_t)w;
+        const int ks = (int)(w32 % (uint32_t)p.ksplit);
+        const int ng = (int)((w32 / (uint32_t)p.ksplit) % (uint32_t)p.n_groups);
+        const int mtile = (int)(w32 / ((uint32_t)p.ksplit * (uint32_t)p.n_groups));
         const int m0 = mtile * 128;
         const int nb_atoms = min(kAtomsB, (p.n_total - ng * 256) / 64);
         const uint32_t tx_bytes = (uint32_t)((kAtomsA + nb_atoms) * p.planes) * p.tile_bytes;
+        int bcb[kAtomsB], bkx[kAtomsB], bky[kAtomsB], bkz[kAtomsB];
+        for (int j = 0; j < kAtomsB; ++j) {
+          const int n = ng * 256 + j * 64;
+          const int tap = n / p.Cb;
+          bcb[j] = n - tap * p.Cb; bkx[j] = (tap & 3) - 1; bky[j] = ((tap >> 2) & 3) - 1; bkz[j] = (tap >> 4) - 1;
+        }
         const int t0 = ks * tps, t1 = min(p.row_tiles, t0 + tps);
         for (int rt = t0; rt < t1; ++rt) {
           mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
           uint64_t* bar = &hdr->full[s];
           const uint32_t base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
           mbar_arrive_expect_tx(bar, tx_bytes);
-          const long long row0 = (long long)rt * p.rs;
+          const uint32_t row0 = (uint32_t)rt * (uint32_t)p.rs;
           for (int at = 0; at < kAtomsA; ++at)
             for (int pl = 0; pl < p.planes; ++pl)
               tma_load_2d(base + (uint32_t)(at * p.planes + pl) * p.tile_bytes, &p.tmA[pl], m0 + at * 64, (int)row0, bar);
           const uint32_t bbase = base + (uint32_t)(kAtomsA * p.planes) * p.tile_bytes;
           int x0 = 0, y0 = 0, z0 = 0, n0 = 0;
           if (p.b_mode == SG_MODE_CONV) {
-            x0 = (int)(row0 % p.gx); long long t = row0 / p.gx;
-            y0 = (int)(t % p.gy); t /= p.gy;
-            z0 = (int)(t % p.gz); n0 = (int)(t / p.gz);
+            x0 = 2 * (int)(row0 & (uint32_t)(p.gx - 1));
+            y0 = 2 * (int)((row0 >> lgx) & (uint32_t)(p.gy - 1));
+            z0 = 2 * (int)((row0 >> (lgx + lgy)) & (uint32_t)(p.gz - 1));
+            n0 = (int)(row0 >> (lgx + lgy + lgz));
           }
           for (int j = 0; j < nb_atoms; ++j) {
-            const int n = ng * 256 + j * 64;
-            const int tap = n / p.Cb, cb = n - tap * p.Cb;
             for (int pl = 0; pl < p.planes; ++pl) {
               const uint32_t dst = bbase + (uint32_t)(j * p.planes + pl) * p.tile_bytes;
-              if (p.b_mode == SG_MODE_DENSE) tma_load_2d(dst, &p.tmB[pl], cb, (int)row0, bar);
-              else tma_load_5d(dst, &p.tmB[pl], cb, 2 * x0 - 1 + (tap & 3), 2 * y0 - 1 + ((tap >> 2) & 3), 2 * z0 - 1 + (tap >> 4), n0, bar);
+              if (p.b_mode == SG_MODE_DENSE) tma_load_2d(dst, &p.tmB[pl], bcb[j], (int)row0, bar);
+              else tma_load_5d(dst, &p.tmB[pl], bcb[j], x0 + bkx[j], y0 + bky[j], z0 + bkz[j], n0, bar);
             }
           }
           if (++s == S) { s = 0; ph ^= 1; }
