@@ -243,6 +243,29 @@ __global__ void sg_rowdot_fwd_kernel(const bf16* x, long long x_ps, int planes, 
     if (lane == 0) y[row] = apply_act(s + b, act);
   }
 }
+// few, very wide rows (Conv3d(256->1,k4,s1): 64 rows x 16384): one block per row
+__global__ void sg_rowdot_fwd_block_kernel(const bf16* x, long long x_ps, int planes, long long rows, int c, const float* w,
+                                           int wc, long long s_t, long long s_c, const float* bias, int act, float* y) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  float s = 0.f;
+  for (int p8 = threadIdx.x; p8 < c / 8; p8 += blockDim.x) {
+    float v[8];
+    load8(x, x_ps, planes, row * c + p8 * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int k = p8 * 8 + j; s += v[j] * __ldg(w + (long long)(k / wc) * s_t + (long long)(k % wc) * s_c); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) y[row] = apply_act(t + (bias ? __ldg(bias) : 0.f), act);
+  }
+}
 // g[r] = gy[r]*act'(y[r]);  gx[r,:] = g[r]*w (planes);  gw[c] += sum_r g[r]*x[r,c];  gb += sum_r g[r]
 __global__ void sg_rowdot_bwd_kernel(const float* gy, const float* y, int act, const bf16* x, long long x_ps, int planes,
                                      long long rows, int c, const float* w, int wc, long long s_t, long long s_c, bf16* gx,
@@ -379,6 +402,45 @@ __global__ void sg_sdf_unpack_grad_kernel(const bf16* ga, long long ga_ps, const
       }
     }
   }
+}
+// indexed variant: each thread owns one piece column and walks a contiguous run of rows, accumulating in registers while
+// the shape index stays the same (points of a shape are contiguous in every caller of the reference) and flushing one
+// atomicAdd per channel per run -- instead of one atomic per point and channel.
+__global__ void sg_sdf_unpack_grad_runs_kernel(const bf16* ga, long long ga_ps, const bf16* gb, long long gb_ps, int planes, long long n,
+                                               int c_src, int L, const int* index, float* gpoints, float* glatent, int rows_per_thread) {
+  const int P8 = (3 + L + 7) / 8;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int p8 = (int)(t % P8);
+  const long long r0 = (t / P8) * rows_per_thread, r1 = min(n, r0 + rows_per_thread);
+  if (r0 >= n) return;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  int cur = index[r0];
+  for (long long row = r0; row < r1; ++row) {
+    const int s = index[row];
+    if (s != cur) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int ch = p8 * 8 + j; if (ch >= 3 && ch < 3 + L) atomicAdd(glatent + (long long)cur * L + (ch - 3), acc[j]); acc[j] = 0.f; }
+      cur = s;
+    }
+    float v[8];
+    load8(ga, ga_ps, planes, row * c_src + p8 * 8, v);
+    if (gb) {
+      float u[8];
+      load8(gb, gb_ps, planes, row * c_src + p8 * 8, u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += u[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = p8 * 8 + j;
+      if (ch < 3) { if (gpoints) gpoints[row * 3 + ch] = v[j]; }
+      else acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const int ch = p8 * 8 + j; if (ch >= 3 && ch < 3 + L) atomicAdd(glatent + (long long)cur * L + (ch - 3), acc[j]); }
 }
 
 // progressive_gan.py:48-50   x = f*x + (1-f)*from_SDF(x_in[:, ::2, ::2, ::2])   (x: [B,r,r,r,C] planes, vol: [B,2r,2r,2r] fp32)
@@ -614,6 +676,11 @@ extern "C" int sg_rowdot_fwd(const void* x, int64_t x_ps, int planes, int64_t ro
   if (rows <= 0) return 0;
   if (c & 7) return sg_fail(-32, "sg_rowdot_fwd: C % 8");
   if (wc <= 0) { wc = c; s_t = 0; s_c = 1; }
+  if (rows <= 2048 && c >= 2048) {
+    sg_rowdot_fwd_block_kernel<<<(int)rows, 256, 0, ST(stream)>>>((const bf16*)x, x_ps, planes, rows, c, w, wc, s_t, s_c, bias, act, y);
+    SG_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   sg_rowdot_fwd_kernel<<<ew_grid(rows * 32, 256), 256, 0, ST(stream)>>>((const bf16*)x, x_ps, planes, rows, c, w, wc, s_t, s_c, bias, act, y);
   SG_CUDA_CHECK_LAUNCH();
   return 0;
@@ -664,6 +731,14 @@ extern "C" int sg_sdf_pack_input(const float* points, const float* latent, const
 extern "C" int sg_sdf_unpack_grad(const void* ga, int64_t ga_ps, const void* gb, int64_t gb_ps, int planes, int64_t n, int c_src, int L,
                                   const int32_t* index, float* gpoints, float* glatent, void* stream) {
   if (n <= 0) return 0;
+  if (index && glatent) {
+    const int P8 = (3 + L + 7) / 8, rpt = 64;
+    const long long threads = ((n + rpt - 1) / rpt) * P8;
+    sg_sdf_unpack_grad_runs_kernel<<<(int)((threads + 255) / 256), 256, 0, ST(stream)>>>((const bf16*)ga, ga_ps, (const bf16*)gb, gb_ps, planes, n,
+                                                                                      c_src, L, index, gpoints, glatent, rpt);
+    SG_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   sg_sdf_unpack_grad_kernel<<<ew_grid(n * ((3 + L + 7) / 8), 256), 256, 0, ST(stream)>>>((const bf16*)ga, ga_ps, (const bf16*)gb, gb_ps,
                                                                                        planes, n, c_src, L, index, gpoints, glatent);
   SG_CUDA_CHECK_LAUNCH();

@@ -23,7 +23,7 @@ namespace sg {
 constexpr int kProducerThreads = 128;
 constexpr int kIgemmThreads = 288;      // 4 producer warps + 1 MMA warp + 4 epilogue warps
 constexpr int kMaxStages = 6;
-constexpr int kSmemHeader = 1024;       // barriers + tmem pointer
+constexpr int kSmemHeader = 2048;       // barriers + tmem pointer + staged bias
 
 struct IgemmP {
   int mode, planes;
@@ -50,6 +50,8 @@ struct SmemHeader {
   uint64_t accfull[2];
   uint64_t accempty[2];
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  float sbias[256];      // bias of the current N tile (epilogue broadcast reads)
 };
 
 __device__ __forceinline__ void decode_work(const IgemmP& p, long long w64, int& cls, int& nt, int& mtile, int& ks) {
@@ -57,6 +59,138 @@ __device__ __forceinline__ void decode_work(const IgemmP& p, long long w64, int&
   if (p.ksplit > 1) { ks = (int)(w % (uint32_t)p.ksplit); w /= (uint32_t)p.ksplit; } else ks = 0;
   mtile = (int)(w % (uint32_t)p.m_tiles); w /= (uint32_t)p.m_tiles;
   if (p.n_tiles > 1) { nt = (int)(w % (uint32_t)p.n_tiles); cls = (int)(w / (uint32_t)p.n_tiles); } else { nt = 0; cls = (int)w; }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, int runtime_act) {
+  if (ACT == ACT_NONE) return v;
+  if (ACT == ACT_LRELU) return v > 0.f ? v : v * kLreluSlope;
+  if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+  return apply_act(v, runtime_act);
+}
+
+// Epilogue warps: TMEM -> registers -> (+bias from smem) -> activation -> bf16 planes / fp32.
+// Fast path (whole N tile valid, 16-byte aligned rows, no mask): ~3 instructions per element, straight-line.
+template <int ACT>
+__device__ __noinline__ void epilogue_role(const IgemmP& p, SmemHeader* hdr, uint32_t tmem_base, int cps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+  const int trow = q * 32 + lane;
+  const int etid = threadIdx.x - 5 * 32;  // 0..127 among the epilogue threads
+  float* sbias = hdr->sbias;
+  int it = 0, staged_nt = -1;
+  for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
+    int cls, nt, mtile, ks;
+    decode_work(p, w, cls, nt, mtile, ks);
+    const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
+    const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
+    const bool add_bias = (p.bias != nullptr) && (ks == 0);
+    if (staged_nt != nt) {               // bias of this N tile -> shared memory (broadcast reads afterwards)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int j = etid; j < p.bn; j += 128) {
+        const int n = nt * p.bn + j;
+        sbias[j] = (p.bias != nullptr && n < p.n_valid) ? __ldg(p.bias + (p.bias_mod > 0 ? n % p.bias_mod : n)) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      staged_nt = nt;
+    }
+    mbar_wait(&hdr->accfull[ab], aph, p.err);
+    tc_fence_after();
+    const bool tile_full = (nt * p.bn + p.bn <= p.n_valid);
+    const bool fast = tile_full && p.mask == nullptr && (p.bn & 31) == 0 &&
+                      ((p.out_kind == SG_OUT_BF16 && (p.out_ld & 7) == 0) || (p.out_kind == SG_OUT_F32 && (p.out_ld & 3) == 0));
+    for (int sub = 0; sub < p.mt; ++sub) {
+      const long long gr = ((long long)mtile * p.mt + sub) * kTileRows + trow;
+      const bool valid = gr < p.rows;
+      long long orow = gr;
+      if (p.mode == SG_MODE_CONVT && valid) {
+        int qw = (int)(gr % p.aW); long long t = gr / p.aW;
+        int qh = (int)(t % p.aH); t /= p.aH;
+        int qd = (int)(t % p.aD); long long n = t / p.aD;
+        orow = ((n * p.oD + 2 * qd + ((cls >> 2) & 1)) * p.oH + 2 * qh + ((cls >> 1) & 1)) * p.oW + 2 * qw + (cls & 1);
+      }
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
+      const long long obase = orow * p.out_ld + (long long)nt * p.bn;
+      if (fast) {
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(t_addr + c0, r);
+          tmem_ld_wait();
+          if (!valid) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = add_bias ? *reinterpret_cast<const float4*>(sbias + c0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = act_t<ACT>(__uint_as_float(r[j]) + b.x, p.act);
+            v[j + 1] = act_t<ACT>(__uint_as_float(r[j + 1]) + b.y, p.act);
+            v[j + 2] = act_t<ACT>(__uint_as_float(r[j + 2]) + b.z, p.act);
+            v[j + 3] = act_t<ACT>(__uint_as_float(r[j + 3]) + b.w, p.act);
+          }
+          if (p.out_kind == SG_OUT_BF16) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + obase + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 hi;
+              hi.x = pack_bf16x2(v[j], v[j + 1]); hi.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              hi.z = pack_bf16x2(v[j + 4], v[j + 5]); hi.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = hi;
+              if (p.planes == 2) {
+                uint4 lo;
+                lo.x = pack_bf16x2(v[j] - bf16lo_to_f(hi.x), v[j + 1] - bf16hi_to_f(hi.x));
+                lo.y = pack_bf16x2(v[j + 2] - bf16lo_to_f(hi.y), v[j + 3] - bf16hi_to_f(hi.y));
+                lo.z = pack_bf16x2(v[j + 4] - bf16lo_to_f(hi.z), v[j + 5] - bf16hi_to_f(hi.z));
+                lo.w = pack_bf16x2(v[j + 6] - bf16lo_to_f(hi.w), v[j + 7] - bf16hi_to_f(hi.w));
+                *reinterpret_cast<uint4*>(o + p.out_ps + j) = lo;
+              }
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + obase + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      } else {
+        // generic path: ragged N, masks, atomics, unaligned rows
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t r[32];
+          __syncwarp();
+          if (c0 + 32 <= p.bn) {
+            tmem_ld32(t_addr + c0, r);
+          } else {
+            uint32_t r16[16];
+            tmem_ld16(t_addr + c0, r16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0; }
+          }
+          tmem_ld_wait();
+          if (!valid) continue;
+          const int ncols = min(32, p.bn - c0);
+          for (int j = 0; j < ncols; ++j) {
+            const int n = nt * p.bn + c0 + j;
+            if (n >= p.n_valid) break;
+            float x = __uint_as_float(r[j]);
+            if (add_bias) x += sbias[c0 + j];
+            x = act_t<ACT>(x, p.act);
+            const long long eoff = obase + c0 + j;
+            if (p.mask) x *= act_grad_from_output(__bfloat162float(p.mask[eoff]), p.mask_act);
+            if (p.out_kind == SG_OUT_BF16) {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + eoff;
+              const bf16 h = __float2bfloat16_rn(x);
+              *o = h;
+              if (p.planes == 2) o[p.out_ps] = __float2bfloat16_rn(x - __bfloat162float(h));
+            } else if (p.out_kind == SG_OUT_F32) {
+              reinterpret_cast<float*>(p.out)[eoff] = x;
+            } else {
+              atomicAdd(reinterpret_cast<float*>(p.out) + eoff, x);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(&hdr->accempty[ab]);
+  }
 }
 
 __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid_constant__ IgemmP p) {
@@ -356,108 +490,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     }
   } else {
     // ================================================================ EPILOGUE
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int trow = q * 32 + lane;
-    int it = 0;
-    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
-      int cls, nt, mtile, ks;
-      decode_work(p, w, cls, nt, mtile, ks);
-      const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
-      const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
-      mbar_wait(&hdr->accfull[ab], aph, p.err);
-      tc_fence_after();
-      const bool add_bias = (p.bias != nullptr) && (ks == 0);
-      for (int sub = 0; sub < p.mt; ++sub) {
-        const long long gr = ((long long)mtile * p.mt + sub) * kTileRows + trow;
-        const bool valid = gr < p.rows;
-        long long orow = gr;
-        if (p.mode == SG_MODE_CONVT && valid) {
-          int qw = (int)(gr % p.aW); long long t = gr / p.aW;
-          int qh = (int)(t % p.aH); t /= p.aH;
-          int qd = (int)(t % p.aD); long long n = t / p.aD;
-          orow = ((n * p.oD + 2 * qd + ((cls >> 2) & 1)) * p.oH + 2 * qh + ((cls >> 1) & 1)) * p.oW + 2 * qw + (cls & 1);
-        }
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
-        for (int c0 = 0; c0 < p.bn; c0 += 32) {
-          uint32_t r[32];
-          __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
-          if (c0 + 32 <= p.bn) {
-            tmem_ld32(t_addr + c0, r);
-          } else {
-            uint32_t r16[16];
-            tmem_ld16(t_addr + c0, r16);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0; }
-          }
-          tmem_ld_wait();
-          if (!valid) continue;
-          const int nb = nt * p.bn + c0;
-          const int ncols = min(32, p.bn - c0);
-#pragma unroll
-          for (int j8 = 0; j8 < 32; j8 += 8) {
-            if (j8 >= ncols) break;
-            const int n = nb + j8;
-            if (n >= p.n_valid) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(r[j8 + j]);
-              if (add_bias && n + j < p.n_valid) x += __ldg(p.bias + (p.bias_mod > 0 ? (n + j) % p.bias_mod : n + j));
-              v[j] = apply_act(x, p.act);
-            }
-            const long long eoff = orow * p.out_ld + n;
-            const bool full8 = (n + 8 <= p.n_valid);
-            if (p.mask) {
-              if (full8 && (p.out_ld & 7) == 0) {
-                const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask + eoff));
-                v[0] *= act_grad_from_output(bf16lo_to_f(m.x), p.mask_act); v[1] *= act_grad_from_output(bf16hi_to_f(m.x), p.mask_act);
-                v[2] *= act_grad_from_output(bf16lo_to_f(m.y), p.mask_act); v[3] *= act_grad_from_output(bf16hi_to_f(m.y), p.mask_act);
-                v[4] *= act_grad_from_output(bf16lo_to_f(m.z), p.mask_act); v[5] *= act_grad_from_output(bf16hi_to_f(m.z), p.mask_act);
-                v[6] *= act_grad_from_output(bf16lo_to_f(m.w), p.mask_act); v[7] *= act_grad_from_output(bf16hi_to_f(m.w), p.mask_act);
-              } else {
-                for (int j = 0; j < 8 && n + j < p.n_valid; ++j)
-                  v[j] *= act_grad_from_output(__bfloat162float(p.mask[eoff + j]), p.mask_act);
-              }
-            }
-            if (p.out_kind == SG_OUT_BF16) {
-              bf16* o = reinterpret_cast<bf16*>(p.out) + eoff;
-              if (full8 && (p.out_ld & 7) == 0) {
-                uint4 hi;
-                hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(o) = hi;
-                if (p.planes == 2) {
-                  uint4 lo;
-                  lo.x = pack_bf16x2(v[0] - bf16lo_to_f(hi.x), v[1] - bf16hi_to_f(hi.x));
-                  lo.y = pack_bf16x2(v[2] - bf16lo_to_f(hi.y), v[3] - bf16hi_to_f(hi.y));
-                  lo.z = pack_bf16x2(v[4] - bf16lo_to_f(hi.z), v[5] - bf16hi_to_f(hi.z));
-                  lo.w = pack_bf16x2(v[6] - bf16lo_to_f(hi.w), v[7] - bf16hi_to_f(hi.w));
-                  *reinterpret_cast<uint4*>(o + p.out_ps) = lo;
-                }
-              } else {
-                for (int j = 0; j < 8 && n + j < p.n_valid; ++j) {
-                  const bf16 h = __float2bfloat16_rn(v[j]);
-                  o[j] = h;
-                  if (p.planes == 2) o[p.out_ps + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-                }
-              }
-            } else if (p.out_kind == SG_OUT_F32) {
-              float* o = reinterpret_cast<float*>(p.out) + eoff;
-              if (full8 && (p.out_ld & 3) == 0) {
-                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                for (int j = 0; j < 8 && n + j < p.n_valid; ++j) o[j] = v[j];
-              }
-            } else {
-              float* o = reinterpret_cast<float*>(p.out) + eoff;
-              for (int j = 0; j < 8 && n + j < p.n_valid; ++j) atomicAdd(o + j, v[j]);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&hdr->accempty[ab]);
+    switch (p.act) {
+      case ACT_NONE: epilogue_role<ACT_NONE>(p, hdr, tmem_base, cps); break;
+      case ACT_LRELU: epilogue_role<ACT_LRELU>(p, hdr, tmem_base, cps); break;
+      case ACT_RELU: epilogue_role<ACT_RELU>(p, hdr, tmem_base, cps); break;
+      default: epilogue_role<-1>(p, hdr, tmem_base, cps); break;
     }
   }
   // ---------------------------------------------------------------- teardown
