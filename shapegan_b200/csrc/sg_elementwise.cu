@@ -559,7 +559,7 @@ static int col_cfg(long long rows, int c, ColCfg& k, const char* who) {
   k.P8 = c / 8;
   k.R = std::max(1, 256 / k.P8);
   k.block = k.P8 * k.R;
-  long long per = (long long)k.R * 32;
+  long long per = (long long)k.R * 4;      // >= 4 rows per thread; small tensors still spread over many blocks
   long long blocks = std::max<long long>(1, std::min<long long>((rows + per - 1) / per, 148 * 8));
   k.rpb = (rows + blocks - 1) / blocks;
   k.grid = (int)((rows + k.rpb - 1) / std::max<long long>(k.rpb, 1));

@@ -54,7 +54,8 @@ struct SmemHeader {
   float sbias[256];      // bias of the current N tile (epilogue broadcast reads)
 };
 
-__device__ __forceinline__ void decode_work(const IgemmP& p, long long w64, int& cls, int& nt, int& mtile, int& ks) {
+template <class P>
+__device__ __forceinline__ void decode_work(const P& p, long long w64, int& cls, int& nt, int& mtile, int& ks) {
   uint32_t w = (uint32_t)w64;              // work_total < 2^31 (checked on the host): 32-bit division only
   if (p.ksplit > 1) { ks = (int)(w % (uint32_t)p.ksplit); w /= (uint32_t)p.ksplit; } else ks = 0;
   mtile = (int)(w % (uint32_t)p.m_tiles); w /= (uint32_t)p.m_tiles;
@@ -71,8 +72,14 @@ __device__ __forceinline__ float act_t(float v, int runtime_act) {
 
 // Epilogue warps: TMEM -> registers -> (+bias from smem) -> activation -> bf16 planes / fp32.
 // Fast path (whole N tile valid, 16-byte aligned rows, no mask): ~3 instructions per element, straight-line.
+struct EpiP {   // the fields the epilogue needs, by value (a reference to the __grid_constant__ struct turns every access into a generic load)
+  int mode, planes, n_valid, bn, mt, ksplit, m_tiles, n_tiles, bias_mod, act, mask_act, out_kind, out_ld, oD, oH, oW, aD, aH, aW, acc_bufs, acc_slot;
+  long long rows, work_total, out_ps;
+  const float* bias; const bf16* mask; char* out; int* err;
+};
+
 template <int ACT>
-__device__ __noinline__ void epilogue_role(const IgemmP& p, SmemHeader* hdr, uint32_t tmem_base, int cps) {
+__device__ __forceinline__ void epilogue_role(const EpiP p, SmemHeader* hdr, uint32_t tmem_base, int cps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
   const int trow = q * 32 + lane;
@@ -490,11 +497,17 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     }
   } else {
     // ================================================================ EPILOGUE
+    EpiP e;
+    e.mode = p.mode; e.planes = p.planes; e.n_valid = p.n_valid; e.bn = p.bn; e.mt = p.mt; e.ksplit = p.ksplit;
+    e.m_tiles = p.m_tiles; e.n_tiles = p.n_tiles; e.bias_mod = p.bias_mod; e.act = p.act; e.mask_act = p.mask_act;
+    e.out_kind = p.out_kind; e.out_ld = p.out_ld; e.oD = p.oD; e.oH = p.oH; e.oW = p.oW; e.aD = p.aD; e.aH = p.aH; e.aW = p.aW;
+    e.acc_bufs = p.acc_bufs; e.acc_slot = p.acc_slot; e.rows = p.rows; e.work_total = p.work_total; e.out_ps = p.out_ps;
+    e.bias = p.bias; e.mask = p.mask; e.out = p.out; e.err = p.err;
     switch (p.act) {
-      case ACT_NONE: epilogue_role<ACT_NONE>(p, hdr, tmem_base, cps); break;
-      case ACT_LRELU: epilogue_role<ACT_LRELU>(p, hdr, tmem_base, cps); break;
-      case ACT_RELU: epilogue_role<ACT_RELU>(p, hdr, tmem_base, cps); break;
-      default: epilogue_role<-1>(p, hdr, tmem_base, cps); break;
+      case ACT_NONE: epilogue_role<ACT_NONE>(e, hdr, tmem_base, cps); break;
+      case ACT_LRELU: epilogue_role<ACT_LRELU>(e, hdr, tmem_base, cps); break;
+      case ACT_RELU: epilogue_role<ACT_RELU>(e, hdr, tmem_base, cps); break;
+      default: epilogue_role<-1>(e, hdr, tmem_base, cps); break;
     }
   }
   // ---------------------------------------------------------------- teardown
