@@ -72,14 +72,21 @@ __device__ __forceinline__ float act_t(float v, int runtime_act) {
 
 // Epilogue warps: TMEM -> registers -> (+bias from smem) -> activation -> bf16 planes / fp32.
 // Fast path (whole N tile valid, 16-byte aligned rows, no mask): ~3 instructions per element, straight-line.
-struct EpiP {   // the fields the epilogue needs, by value (a reference to the __grid_constant__ struct turns every access into a generic load)
+struct EpiP {   // the fields the epilogue needs, copied ONCE into registers: the kernel parameter is reached through a
+                // reference here, and every p.field access would otherwise be a generic load with a long-scoreboard stall
   int mode, planes, n_valid, bn, mt, ksplit, m_tiles, n_tiles, bias_mod, act, mask_act, out_kind, out_ld, oD, oH, oW, aD, aH, aW, acc_bufs, acc_slot;
   long long rows, work_total, out_ps;
   const float* bias; const bf16* mask; char* out; int* err;
 };
 
 template <int ACT>
-__device__ __forceinline__ void epilogue_role(const EpiP p, SmemHeader* hdr, uint32_t tmem_base, int cps) {
+__device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, uint32_t tmem_base, int cps) {
+  EpiP p;
+  p.mode = gp.mode; p.planes = gp.planes; p.n_valid = gp.n_valid; p.bn = gp.bn; p.mt = gp.mt; p.ksplit = gp.ksplit;
+  p.m_tiles = gp.m_tiles; p.n_tiles = gp.n_tiles; p.bias_mod = gp.bias_mod; p.act = gp.act; p.mask_act = gp.mask_act;
+  p.out_kind = gp.out_kind; p.out_ld = gp.out_ld; p.oD = gp.oD; p.oH = gp.oH; p.oW = gp.oW; p.aD = gp.aD; p.aH = gp.aH; p.aW = gp.aW;
+  p.acc_bufs = gp.acc_bufs; p.acc_slot = gp.acc_slot; p.rows = gp.rows; p.work_total = gp.work_total; p.out_ps = gp.out_ps;
+  p.bias = gp.bias; p.mask = gp.mask; p.out = gp.out; p.err = gp.err;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
   const int trow = q * 32 + lane;
@@ -497,17 +504,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     }
   } else {
     // ================================================================ EPILOGUE
-    EpiP e;
-    e.mode = p.mode; e.planes = p.planes; e.n_valid = p.n_valid; e.bn = p.bn; e.mt = p.mt; e.ksplit = p.ksplit;
-    e.m_tiles = p.m_tiles; e.n_tiles = p.n_tiles; e.bias_mod = p.bias_mod; e.act = p.act; e.mask_act = p.mask_act;
-    e.out_kind = p.out_kind; e.out_ld = p.out_ld; e.oD = p.oD; e.oH = p.oH; e.oW = p.oW; e.aD = p.aD; e.aH = p.aH; e.aW = p.aW;
-    e.acc_bufs = p.acc_bufs; e.acc_slot = p.acc_slot; e.rows = p.rows; e.work_total = p.work_total; e.out_ps = p.out_ps;
-    e.bias = p.bias; e.mask = p.mask; e.out = p.out; e.err = p.err;
     switch (p.act) {
-      case ACT_NONE: epilogue_role<ACT_NONE>(e, hdr, tmem_base, cps); break;
-      case ACT_LRELU: epilogue_role<ACT_LRELU>(e, hdr, tmem_base, cps); break;
-      case ACT_RELU: epilogue_role<ACT_RELU>(e, hdr, tmem_base, cps); break;
-      default: epilogue_role<-1>(e, hdr, tmem_base, cps); break;
+      case ACT_NONE: epilogue_role<ACT_NONE>(p, hdr, tmem_base, cps); break;
+      case ACT_LRELU: epilogue_role<ACT_LRELU>(p, hdr, tmem_base, cps); break;
+      case ACT_RELU: epilogue_role<ACT_RELU>(p, hdr, tmem_base, cps); break;
+      default: epilogue_role<-1>(p, hdr, tmem_base, cps); break;
     }
   }
   // ---------------------------------------------------------------- teardown
