@@ -178,6 +178,24 @@ int sg_clamp(float* p, int64_t n, float lo, float hi, void* stream);
 int sg_sum_f32(const float* x, int64_t n, double* out, void* stream);
 int sg_l1_loss_grad(const float* out, const float* target, float* gout, int64_t n, double* loss_sum, void* stream);
 
+/* Fused persistent DeepSDF MLP forward (model/sdf_net.py:56-61, latent_code_size 128, bf16 operands): all 8 layers of a
+ * tile pair in one CTA.  w_img = 28 weight chunks of 32 KB in stream order (sg_pack_b images of
+ * L1[:,3:131] | L2 | L3 | L4 | L5[:,0:256] | L5[:,259:387] | L6 | L7); aux = fp32 {float4[256] (wx,wy,wz,b) of L1,
+ * same of L5, bias[5][256] of L2,L3,L4,L6,L7, w8[256], b8}; stash (optional) receives the 7 hidden activations as
+ * bf16 [7][n][256] for the backward pass.  replaces: the 8 F.linear + 2 torch.cat + ReLU/Tanh launches of SDFNet.forward */
+typedef struct {
+  const float* points;
+  const float* latent;
+  const int32_t* index; /* NULL: latent row i belongs to point i */
+  int64_t n;
+  const void* w_img;
+  const float* aux;
+  float* out;
+  void* stash;
+} sg_sdfnet_fwd_args;
+int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream);
+int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32_t* aux_floats);
+
 /* ---- misc ---- */
 int sg_abi_version(void);
 const char* sg_last_error(void);

@@ -44,6 +44,11 @@ class SgPackBArgs(ctypes.Structure):
                 ('s_tap', c_int64), ('s_c', c_int64)]
 
 
+class SgSdfnetFwdArgs(ctypes.Structure):
+    _fields_ = [('points', c_void_p), ('latent', c_void_p), ('index', c_void_p), ('n', c_int64), ('w_img', c_void_p),
+                ('aux', c_void_p), ('out', c_void_p), ('stash', c_void_p)]
+
+
 # every symbol include/sg_b200.h declares, with (restype, argtypes); tests check that all of them resolve
 SYMBOLS = {
     'sg_abi_version': (c_int32, []),
@@ -58,6 +63,8 @@ SYMBOLS = {
     'sg_wgrad_reduce': (c_int32, [ctypes.POINTER(SgWgradReduceArgs), c_void_p]),
     'sg_pack_b_bytes': (c_size_t, [ctypes.POINTER(SgPackBArgs)]),
     'sg_pack_b': (c_int32, [ctypes.POINTER(SgPackBArgs), c_void_p]),
+    'sg_sdfnet_fwd': (c_int32, [ctypes.POINTER(SgSdfnetFwdArgs), c_void_p]),
+    'sg_sdfnet_fwd_layout': (c_int32, [ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
     # p = pointer, l = int64, i = int32, f = float (see _sig)
     'sg_act_bwd': 'plplpliliipp',
     'sg_bn_stats': 'plilipp',

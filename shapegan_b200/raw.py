@@ -47,14 +47,18 @@ def null_tensor():
 
 # ------------------------------------------------------------------------------------------------- weight packing
 def pack_b(w, planes, n_valid, k_pad, taps, c_count, c_valid, s_n0, s_tap, s_c, classes=1, n0_count=None, s_n1=0,
-           n_pad=None):
+           n_pad=None, out=None):
     _require_cuda(w)
     assert w.dtype == torch.float32      # may be a strided view: all addressing goes through the explicit strides
     n_pad = round_up(n_valid, 16) if n_pad is None else n_pad
     a = L.SgPackBArgs(ctypes.c_void_p(w.data_ptr()), None, planes, classes, n_pad, n_valid,
                       n0_count if n0_count is not None else n_pad, s_n1, s_n0, k_pad, taps, c_count, c_valid, s_tap, s_c)
     nbytes = L.lib().sg_pack_b_bytes(ctypes.byref(a))
-    img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    if out is not None:
+        assert out.numel() == nbytes and out.dtype == torch.uint8
+        img = out
+    else:
+        img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     a.image = ctypes.c_void_p(img.data_ptr())
     L.check(L.lib().sg_pack_b(ctypes.byref(a), stream()), 'sg_pack_b')
     return img
@@ -331,4 +335,12 @@ def l1_loss_grad(out, target, want_grad=True):
 def sum_f32(x):
     out = dsums(1, x.device)
     _call('sg_sum_f32', _p(x), x.numel(), _p(out))
+    return out
+
+
+def sdfnet_fwd(points, latent, index, w_img, aux, stash=None):
+    n = points.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=points.device)
+    a = L.SgSdfnetFwdArgs(_p(points), _p(latent), _p(index), n, _p(w_img), _p(aux), _p(out), _p(stash))
+    L.check(L.lib().sg_sdfnet_fwd(ctypes.byref(a), stream()), 'sg_sdfnet_fwd')
     return out
