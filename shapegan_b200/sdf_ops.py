@@ -86,7 +86,7 @@ class SDFNetFunction(Function):
         b = [params[2 * i + 1] for i in range(8)]
         points = points.contiguous()
         latent = latent.contiguous()
-        need_graph = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        need_graph = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
         if planes == 1 and lat == 128 and fused_enabled():
             # fused persistent kernel: all 8 layers per tile pair in one CTA (sg_sdfnet.cu)
             img, aux = _fused_pack(w, b)
