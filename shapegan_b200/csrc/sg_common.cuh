@@ -185,6 +185,46 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 __device__ __forceinline__ float bf16lo_to_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi_to_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// Conv3d(1->C,k4,s2,p1) im2col for EIGHT consecutive output-x voxels (same n, od, oh) of piece g = taps (kd = g>>1,
+// kh = 2(g&1)+{0,1}, kw = 0..3): two input lines, each fetched with 10 aligned float2 loads, feed all 8 rows x 8 taps.
+// Needs W % 16 == 0 (so 8 outputs never straddle a line and float2 pairs never straddle the border).
+__device__ __forceinline__ void patch_fill8(const float* vol_n, int D, int H, int W, int od, int oh, int ow0, int g, bool valid,
+                                            uint8_t* tile_hi, uint8_t* tile_lo, int row0) {
+  const int kd = g >> 1, kh0 = (g & 1) * 2;
+  const int d = 2 * od - 1 + kd;
+  float f[2][20];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int h = 2 * oh - 1 + kh0 + hh;
+    const bool lv = valid && d >= 0 && d < D && h >= 0 && h < H;
+    const float2* line = reinterpret_cast<const float2*>(vol_n + ((size_t)(lv ? d : 0) * H + (lv ? h : 0)) * W) + (ow0 - 1);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const int w = 2 * ow0 - 2 + 2 * j;
+      float2 v = make_float2(0.f, 0.f);
+      if (lv && w >= 0 && w < W) v = __ldg(line + j);
+      f[hh][2 * j] = v.x; f[hh][2 * j + 1] = v.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a0 = f[0][2 * i + 1], a1 = f[0][2 * i + 2], a2 = f[0][2 * i + 3], a3 = f[0][2 * i + 4];
+    const float b0 = f[1][2 * i + 1], b1 = f[1][2 * i + 2], b2 = f[1][2 * i + 3], b3 = f[1][2 * i + 4];
+    uint4 hi;
+    hi.x = pack_bf16x2(a0, a1); hi.y = pack_bf16x2(a2, a3); hi.z = pack_bf16x2(b0, b1); hi.w = pack_bf16x2(b2, b3);
+    const uint32_t off = sw128((uint32_t)(row0 + i), (uint32_t)g);
+    *reinterpret_cast<uint4*>(tile_hi + off) = hi;
+    if (tile_lo) {
+      uint4 lo;
+      lo.x = pack_bf16x2(a0 - bf16lo_to_f(hi.x), a1 - bf16hi_to_f(hi.x));
+      lo.y = pack_bf16x2(a2 - bf16lo_to_f(hi.y), a3 - bf16hi_to_f(hi.y));
+      lo.z = pack_bf16x2(b0 - bf16lo_to_f(hi.z), b1 - bf16hi_to_f(hi.z));
+      lo.w = pack_bf16x2(b2 - bf16lo_to_f(hi.w), b3 - bf16hi_to_f(hi.w));
+      *reinterpret_cast<uint4*>(tile_lo + off) = lo;
+    }
+  }
+}
+
 // activations used on the path
 enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -352,7 +352,22 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
         mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
         uint8_t* st = stage0 + (size_t)s * p.stage_bytes;
         const uint32_t a_base = smem_u32(st);
-        if (p.mode == SG_MODE_PATCH) {
+        if (p.mode == SG_MODE_PATCH && (p.aW & 15) == 0) {
+          // fast im2col: thread (rg = tid>>3, g) fills 8 consecutive output-x rows of piece g from two register-blocked lines
+          const float* vol = reinterpret_cast<const float*>(p.a_ptr);
+          const int oW = p.aW >> 1, oH = p.aH >> 1, oD = p.aD >> 1;
+          for (int sub = 0; sub < p.mt; ++sub) {
+            const long long gr0 = ((long long)mtile * p.mt + sub) * kTileRows + rb * 8;
+            const bool v = gr0 < p.rows;
+            const uint32_t r32 = (uint32_t)(v ? gr0 : 0);
+            const int ow0 = (int)(r32 % (uint32_t)oW); uint32_t t2 = r32 / (uint32_t)oW;
+            const int oh = (int)(t2 % (uint32_t)oH); t2 /= (uint32_t)oH;
+            const int od = (int)(t2 % (uint32_t)oD); const uint32_t n = t2 / (uint32_t)oD;
+            uint8_t* tile = st + (size_t)(sub * p.planes) * kTileBytes;
+            patch_fill8(vol + (size_t)n * p.aD * p.aH * p.aW, p.aD, p.aH, p.aW, od, oh, ow0, g, v, tile,
+                        p.planes == 2 ? tile + kTileBytes : nullptr, rb * 8);
+          }
+        } else if (p.mode == SG_MODE_PATCH) {
           // single-channel fp32 volume: K = 64 taps, piece g = taps [8g, 8g+8) = (kd = g>>1, kh = 2(g&1)+{0,1}, kw = 0..3)
           const float* vol = reinterpret_cast<const float*>(p.a_ptr);
           const int kd = g >> 1, khb = (g & 1) * 2;

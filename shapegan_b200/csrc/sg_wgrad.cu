@@ -141,6 +141,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
         mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
         uint8_t* st = stage0 + (size_t)s * p.stage_bytes;
         const uint32_t base = smem_u32(st);
+        const bool patch8 = (p.b_mode == SG_MODE_PATCH) && ((p.bW & 15) == 0);
+        if (patch8 && rb * 8 < p.rs) {
+          // B atom 0 = im2col patches: 8 consecutive output-x rows of piece g per thread (see patch_fill8)
+          const long long gr0 = (long long)rt * p.rs + rb * 8;
+          const bool v = gr0 < p.rows;
+          const uint32_t r32 = (uint32_t)(v ? gr0 : 0);
+          const int ow0 = (int)(r32 % (uint32_t)oW); uint32_t t2 = r32 / (uint32_t)oW;
+          const int oh = (int)(t2 % (uint32_t)oH); t2 /= (uint32_t)oH;
+          const int od = (int)(t2 % (uint32_t)oD); const uint32_t n = t2 / (uint32_t)oD;
+          uint8_t* tile = st + (size_t)(kAtomsA * p.planes) * p.tile_bytes;
+          patch_fill8(reinterpret_cast<const float*>(p.b_ptr) + (size_t)n * p.bD * p.bH * p.bW, p.bD, p.bH, p.bW, od, oh, ow0, g, v, tile,
+                      p.planes == 2 ? tile + p.tile_bytes : nullptr, rb * 8);
+        }
         for (int i = 0; i < rpi; ++i) {
           const int row = rb + 16 * i;
           const long long gr = (long long)rt * p.rs + row;
@@ -157,7 +170,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
           }
           // ---- B atoms
           const uint32_t bbase = base + (uint32_t)(kAtomsA * p.planes) * p.tile_bytes;
-          if (p.b_mode == SG_MODE_PATCH) {
+          if (p.b_mode == SG_MODE_PATCH && patch8) {
+            // filled above
+          } else if (p.b_mode == SG_MODE_PATCH) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;

@@ -75,7 +75,7 @@ class SDFNetFunction(Function):
     then the 16 parameters in state_dict order (layers1.{0,2,4,6}.{weight,bias}, layers2.{0,2,4,6}.{weight,bias})."""
 
     @staticmethod
-    def forward(ctx, points, latent, index, *params):
+    def forward(ctx, points, latent, index, want_grad, *params):
         planes = config.planes()
         n = points.shape[0]
         dev = points.device
@@ -86,7 +86,7 @@ class SDFNetFunction(Function):
         b = [params[2 * i + 1] for i in range(8)]
         points = points.contiguous()
         latent = latent.contiguous()
-        need_graph = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
+        need_graph = bool(want_grad)      # decided by the caller: grad mode is always off inside Function.forward
         if planes == 1 and lat == 128 and fused_enabled():
             # fused persistent kernel: all 8 layers per tile pair in one CTA (sg_sdfnet.cu)
             img, aux = _fused_pack(w, b)
@@ -141,8 +141,8 @@ class SDFNetFunction(Function):
         dev = gout.device
         need_points = ctx.needs_input_grad[0]
         need_latent = ctx.needs_input_grad[1]
-        need_w = [ctx.needs_input_grad[3 + 2 * i] for i in range(8)]
-        need_b = [ctx.needs_input_grad[4 + 2 * i] for i in range(8)]
+        need_w = [ctx.needs_input_grad[4 + 2 * i] for i in range(8)]
+        need_b = [ctx.needs_input_grad[5 + 2 * i] for i in range(8)]
         gw = [None] * 8
         gb = [None] * 8
         gout = gout.contiguous()
@@ -195,7 +195,7 @@ class SDFNetFunction(Function):
             if need_latent:
                 glatent = torch.zeros((lat_rows, lat), dtype=torch.float32, device=dev) if indexed else f32((n, lat))
             raw.sdf_unpack_grad(gx_a, gx_b, cin8, lat, index if indexed else None, gpoints, glatent)
-        grads = [gpoints, glatent, None]
+        grads = [gpoints, glatent, None, None]
         for i in range(8):
             grads.append(gw[i])
             grads.append(gb[i])
@@ -209,4 +209,5 @@ def _wgrad_input(planes, g, x_in, cin, cin8, n, grad_view, ld):
 
 
 def sdfnet_apply(points, latent, index, params):
-    return SDFNetFunction.apply(points, latent, index, *params)
+    want_grad = torch.is_grad_enabled() and (points.requires_grad or latent.requires_grad or any(p.requires_grad for p in params))
+    return SDFNetFunction.apply(points, latent, index, want_grad, *params)
