@@ -481,11 +481,40 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
   return 0;
 }
 
+// many splits, few outputs (e.g. the 64x64 filter of Conv3d(1->64) reduced over 148 row splits): one warp per output element
+__global__ void sg_wgrad_reduce_warp_kernel(const sg_wgrad_reduce_args a) {
+  const long long n_total = (long long)a.taps * a.cb;
+  const long long total = (long long)a.m_valid * n_total;
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; i < total; i += warps) {
+    const int m = (int)(i / n_total);
+    const int n = (int)(i - (long long)m * n_total);
+    const int tap = n / a.cb, c = n - tap * a.cb;
+    if (a.c_valid > 0 && c >= a.c_valid) continue;
+    float acc = 0.f;
+    for (int s = lane; s < a.ksplit; s += 32) acc += a.partials[((size_t)s * a.m_pad + m) * n_total + n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float* g = a.grad + (long long)m * a.sm + (long long)tap * a.st + (long long)c * a.sc;
+      acc *= a.scale;
+      *g = a.accumulate ? (*g + acc) : acc;
+    }
+  }
+}
+
 extern "C" int sg_wgrad_reduce(const sg_wgrad_reduce_args* a, void* stream) {
   if (!a || !a->partials || !a->grad) return sg_fail(-1, "sg_wgrad_reduce: null");
   const long long total = (long long)a->m_valid * a->taps * a->cb;
   if (total <= 0) return 0;
   const int block = 256;
+  if (a->ksplit >= 16 && total <= (1 << 16)) {
+    const int grid = (int)std::min<long long>((total * 32 + block - 1) / block, 148 * 16);
+    sg_wgrad_reduce_warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+    SG_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   const int grid = (int)std::min<long long>((total + block - 1) / block, 148 * 16);
   sg_wgrad_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   SG_CUDA_CHECK_LAUNCH();

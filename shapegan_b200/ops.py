@@ -124,12 +124,15 @@ class ConvOp(LinOp):
                   out_dims=(2 * d, 2 * h, 2 * wd))
         return gx
 
-    def wgrad(self, x, g, w_shape):
+    def wgrad(self, x, g, w_shape, into=None):
         p, b, d, h, wd, c = x.shape
-        gw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
+        gw = into if into is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         raw.wgrad(L.MODE_CONV, p, g, self.cout, x, (b, d, h, wd, c), g[0].numel() // self.cout, gw,
-                  sm=self.cin * 64, st=1, sc=64, m_valid=self.cout)
+                  sm=self.cin * 64, st=1, sc=64, m_valid=self.cout, accumulate=into is not None)
         return gw
+
+    def wgrad_into(self, x, g, grad):
+        self.wgrad(x, g, None, into=grad)
 
     def out_channels(self):
         return self.cout
@@ -197,12 +200,15 @@ class ConvTOp(LinOp):
         raw.igemm(L.MODE_CONV, p, g, (b, d, h, wd, c), rows, 64 * c, img, self.cin, gx, self.cin)
         return gx
 
-    def wgrad(self, x, g, w_shape):
+    def wgrad(self, x, g, w_shape, into=None):
         p, b, d, h, wd, c = g.shape
-        gw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
+        gw = into if into is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         raw.wgrad(L.MODE_CONV, p, x, self.cin, g, (b, d, h, wd, c), x[0].numel() // self.cin, gw,
-                  sm=self.cout * 64, st=1, sc=64, m_valid=self.cin)
+                  sm=self.cout * 64, st=1, sc=64, m_valid=self.cin, accumulate=into is not None)
         return gw
+
+    def wgrad_into(self, x, g, grad):
+        self.wgrad(x, g, None, into=grad)
 
     def out_channels(self):
         return self.cout
@@ -344,7 +350,14 @@ class _Fwd(Function):
         c = op.out_channels()
         g = _MaskMul.apply(gy, y, ctx.act, c) if ctx.act != ACT_NONE else gy
         gx = _Tr.apply(op, g, w) if ctx.needs_input_grad[1] else None
-        gw = _Wgrad.apply(op, x, g, w) if ctx.needs_input_grad[2] else None
+        gw = None
+        if ctx.needs_input_grad[2]:
+            if (not torch.is_grad_enabled()) and w.grad is not None and w.grad.is_contiguous() and hasattr(op, 'wgrad_into'):
+                # first-order backward with an allocated .grad (e.g. the flat gradient arena): accumulate in place, exactly
+                # what AccumulateGrad would do with the returned tensor, minus the temporary and the extra add kernel
+                op.wgrad_into(x, g, w.grad)
+            else:
+                gw = _Wgrad.apply(op, x, g, w)
         gb = None
         if ctx.has_bias and ctx.needs_input_grad[3]:
             # the bias gradient is never differentiated again on this path (the GP contributes exactly zero to biases)

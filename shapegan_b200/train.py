@@ -106,8 +106,16 @@ class WGANStep:
         closs.backward()                                               # :69
         self.copt.step()                                               # :70-71 (clip fused)
         self.gopt.zero_grad(); self.copt.zero_grad()                    # :75-76
-        gloss = -torch.mean(cri(gen(z_gen)))                           # :78-82
-        gloss.backward()                                               # :83
+        # The reference's backward here also fills the critic's weight gradients, which :62-63 of the next batch zeroes
+        # unread.  Same update without that dead work: the critic parameters do not require grad during this backward.
+        for q in self.copt.params:
+            q.requires_grad_(False)
+        try:
+            gloss = -torch.mean(cri(gen(z_gen)))                       # :78-82
+            gloss.backward()                                           # :83
+        finally:
+            for q in self.copt.params:
+                q.requires_grad_(True)
         self.gopt.step()                                               # :84
         return closs.detach(), gloss.detach()
 
