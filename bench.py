@@ -87,6 +87,7 @@ def synth_voxels(b, seed):
 def dist_setup(n):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
         import torch.distributed as dist
         local = int(os.environ.get('LOCAL_RANK', '0'))
         torch.cuda.set_device(local)
