@@ -13,6 +13,7 @@
 //   The xyz columns of layers 1 and 5 (K = 3) and all biases are applied in fp32 in the epilogue; layer 8 (256 -> 1) + tanh is a
 //   per-row dot product folded into the epilogue of layer 7.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "sg_common.cuh"
@@ -39,7 +40,7 @@ struct SdfHdr {
 
 struct SdfP {
   const float* points; const float* latent; const int* index; long long n;
-  const char* w_img; float* out; bf16* stash;
+  const char* w_img; const float* aux; float* out; bf16* stash;
   long long pairs;
   int* err;
 };
@@ -53,19 +54,29 @@ constexpr int kAuxB8 = kAuxW8 + 256;
 constexpr int kAuxFloats = kAuxB8 + 4;
 __constant__ float c_sdf_aux[kAuxFloats];
 
-// one 16-column block of the epilogue: +bias (/ +xyz) -> ReLU -> bf16 -> SMEM operand tile (+ HBM stash) or the layer-8 dot
+// one 16-column block of the epilogue: +bias (/ +xyz) -> ReLU -> bf16 -> SMEM operand tile (+ HBM stash) or the layer-8 dot.
+// kConstAux: aux block read from __constant__ memory (indexed LDC) or from global memory (broadcast LDG.128).
+template <bool kConstAux>
 __device__ __forceinline__ void sdf_epi16(const uint32_t (&acc)[16], int c, int l, bool xyz, int xoff, int boff, float px, float py,
-                                          float pz, uint8_t* hbuf, int r, bf16* srow, float& dot) {
+                                          float pz, uint8_t* hbuf, int r, bf16* srow, float& dot, const float* gaux) {
   float v[16];
   if (xyz) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float4 w = *reinterpret_cast<const float4*>(&c_sdf_aux[xoff + 4 * (c + j)]);
+      const float4 w = kConstAux ? *reinterpret_cast<const float4*>(&c_sdf_aux[xoff + 4 * (c + j)])
+                                 : __ldg(reinterpret_cast<const float4*>(gaux + xoff) + c + j);
       v[j] = fmaxf(__uint_as_float(acc[j]) + w.w + w.x * px + w.y * py + w.z * pz, 0.f);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(acc[j]) + c_sdf_aux[boff + c + j], 0.f);
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = kConstAux ? *reinterpret_cast<const float4*>(&c_sdf_aux[boff + c + j])
+                                 : __ldg(reinterpret_cast<const float4*>(gaux + boff + c + j));
+      v[j] = fmaxf(__uint_as_float(acc[j]) + b.x, 0.f);
+      v[j + 1] = fmaxf(__uint_as_float(acc[j + 1]) + b.y, 0.f);
+      v[j + 2] = fmaxf(__uint_as_float(acc[j + 2]) + b.z, 0.f);
+      v[j + 3] = fmaxf(__uint_as_float(acc[j + 3]) + b.w, 0.f);
+    }
   }
   uint4 pk[2];
 #pragma unroll
@@ -80,7 +91,11 @@ __device__ __forceinline__ void sdf_epi16(const uint32_t (&acc)[16], int c, int 
   } else {
     // layers2.6 (256 -> 1) on the bf16-rounded activations (what the backward sees in the stash)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dot += bf16_round(v[j]) * c_sdf_aux[kAuxW8 + c + j];
+    for (int j = 0; j < 16; j += 4) {
+      const float4 w = kConstAux ? *reinterpret_cast<const float4*>(&c_sdf_aux[kAuxW8 + c + j])
+                                 : __ldg(reinterpret_cast<const float4*>(gaux + kAuxW8 + c + j));
+      dot += bf16_round(v[j]) * w.x + bf16_round(v[j + 1]) * w.y + bf16_round(v[j + 2]) * w.z + bf16_round(v[j + 3]) * w.w;
+    }
   }
   if (srow) {
     *reinterpret_cast<uint4*>(srow + c) = pk[0];
@@ -88,6 +103,7 @@ __device__ __forceinline__ void sdf_epi16(const uint32_t (&acc)[16], int c, int 
   }
 }
 
+template <bool kConstAux>
 __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __grid_constant__ SdfP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SdfHdr* hdr = reinterpret_cast<SdfHdr*>(smem);
@@ -227,12 +243,12 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         for (int c0 = 0; c0 < 256; c0 += 32) {
           tmem_ld_wait();
           tmem_ld16(t_addr + c0 + 16, a1);                 // next 16 columns in flight while these are processed
-          sdf_epi16(a0, c0, l, xyz, xoff, boff, px, py, pz, hbuf, r, srow, dot);
+          sdf_epi16<kConstAux>(a0, c0, l, xyz, xoff, boff, px, py, pz, hbuf, r, srow, dot, p.aux);
           tmem_ld_wait();
           if (c0 + 32 < 256) tmem_ld16(t_addr + c0 + 32, a0);
-          sdf_epi16(a1, c0 + 16, l, xyz, xoff, boff, px, py, pz, hbuf, r, srow, dot);
+          sdf_epi16<kConstAux>(a1, c0 + 16, l, xyz, xoff, boff, px, py, pz, hbuf, r, srow, dot, p.aux);
         }
-        if (l == 7 && valid) p.out[gr] = tanhf(dot + c_sdf_aux[kAuxB8]);
+        if (l == 7 && valid) p.out[gr] = tanhf(dot + (kConstAux ? c_sdf_aux[kAuxB8] : __ldg(p.aux + kAuxB8)));
         if (l < 7) fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
         tc_fence_before();
         mbar_arrive(&hdr->h_ready[t]);
@@ -254,8 +270,10 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   SdfP p;
   memset(&p, 0, sizeof(p));
   p.points = a->points; p.latent = a->latent; p.index = a->index; p.n = a->n;
-  p.w_img = (const char*)a->w_img; p.out = a->out; p.stash = (bf16*)a->stash;
-  {  // the aux block (16 KB) lives in __constant__ memory: stream-ordered device-to-device copy, graph capturable
+  p.w_img = (const char*)a->w_img; p.aux = a->aux; p.out = a->out; p.stash = (bf16*)a->stash;
+  static int const_aux = -1;
+  if (const_aux < 0) { const char* e = getenv("SG_B200_SDF_CONST_AUX"); const_aux = (e && e[0] == '1') ? 1 : 0; }
+  if (const_aux) {  // aux block (16 KB) in __constant__ memory: stream-ordered device-to-device copy, graph capturable
     cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_aux, a->aux, (size_t)(kAuxB8 + 1) * sizeof(float), 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
   }
@@ -264,12 +282,14 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   p.err = sg_error_word();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
+    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
   const int grid = (int)std::min<long long>(p.pairs, sg_num_sms());
-  sg_sdfnet_fwd_kernel<<<grid, kSdfThreads, kSdfSmem, (cudaStream_t)stream>>>(p);
+  if (const_aux) sg_sdfnet_fwd_kernel<true><<<grid, kSdfThreads, kSdfSmem, (cudaStream_t)stream>>>(p);
+  else sg_sdfnet_fwd_kernel<false><<<grid, kSdfThreads, kSdfSmem, (cudaStream_t)stream>>>(p);
   SG_CUDA_CHECK_LAUNCH();
   return 0;
 }
