@@ -172,6 +172,55 @@ class AutodecoderStep:
         return loss.detach()
 
 
+class HybridProgressiveStep:
+    """train_hybrid_progressive_gan.py:134-166: SDFNet generator evaluated on the R^3 grid of every sample (latents broadcast by
+    shape index instead of `.repeat`, :92), progressive discriminator, WGAN-GP, RMSprop 1e-4 for both (:81-82).
+    `generator_update` is the every-5th-batch branch (:136-146); `discriminator_update` is :153-166."""
+
+    def __init__(self, generator, discriminator, iteration, lr=0.0001, gp_weight=10.0, world_size=1):
+        from .nn.progressive_gan import RESOLUTIONS
+        from .nn.sdf_net import get_voxel_coordinates
+        self.gen, self.dis, self.gp_weight = generator, discriminator, gp_weight
+        discriminator.set_iteration(iteration)
+        self.r = RESOLUTIONS[iteration]
+        dev = next(generator.parameters()).device
+        self.grid = get_voxel_coordinates(self.r, return_torch_tensor=True, device=dev)     # :95
+        self.gopt = FlatOptimizer(generator.parameters(), 'rmsprop', lr, world_size=world_size)
+        self.dopt = FlatOptimizer(discriminator.parameters(), 'rmsprop', lr, world_size=world_size)
+        self._cache = {}
+
+    def generate(self, z):
+        b, g = z.shape[0], self.grid.shape[0]
+        if b not in self._cache:
+            self._cache[b] = (self.grid.repeat((b, 1)), torch.arange(b, device=z.device, dtype=torch.int32).repeat_interleave(g))
+        pts, idx = self._cache[b]
+        return self.gen(pts, z, idx).reshape(-1, self.r, self.r, self.r)              # :139-140
+
+    def generator_update(self, z):
+        self.gopt.zero_grad(); self.dopt.zero_grad()
+        for q in self.dopt.params:                       # the critic's weight gradients are discarded by :158 (zero_grad)
+            q.requires_grad_(False)
+        try:
+            loss = -self.dis(self.generate(z)).mean()                                  # :143-144
+            loss.backward()
+        finally:
+            for q in self.dopt.params:
+                q.requires_grad_(True)
+        self.gopt.step()                                                               # :146
+        return loss.detach()
+
+    def discriminator_update(self, valid, z, alpha):
+        self.gopt.zero_grad(); self.dopt.zero_grad()                                    # :153
+        with torch.no_grad():                            # the reference back-propagates into G here and discards it (:136)
+            fake = self.generate(z)
+        out_fake, out_valid = self.dis(fake), self.dis(valid)                          # :157,160
+        gp = gradient_penalty(self.dis, valid, fake, alpha, self.gp_weight)            # :162
+        loss = out_fake.mean() - out_valid.mean() + gp                                 # :163
+        loss.backward()
+        self.dopt.step()                                                               # :166
+        return loss.detach(), gp.detach()
+
+
 class VAEStep:
     """train_autoencoder.py:98-117."""
 
