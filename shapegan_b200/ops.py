@@ -314,19 +314,24 @@ def _bias_grad(g, c):
 
 class _MaskMul(Function):
     """g = ga * act'(y) with y the stored activation OUTPUT (piecewise-linear acts: the mask is a constant of the
-    double backward, so this Function is its own derivative)."""
+    double backward, so this Function is its own derivative).  The same pass can emit the column sums of g (the bias
+    gradient), returned as a non-differentiable second output."""
 
     @staticmethod
-    def forward(ctx, ga, y, act, c):
+    def forward(ctx, ga, y, act, c, want_bias):
         ctx.act, ctx.c = act, c
         ctx.save_for_backward(y)
-        g, _ = raw.act_bwd(ga.contiguous(), y, act, c)
-        return g
+        g, sums = raw.act_bwd(ga.contiguous(), y, act, c, want_sums=want_bias)
+        gb = torch.empty(c if want_bias else 0, dtype=torch.float32, device=ga.device)
+        if want_bias:
+            raw.emit_sums(sums, gb, c)
+        ctx.mark_non_differentiable(gb)
+        return g, gb
 
     @staticmethod
-    def backward(ctx, gg):
+    def backward(ctx, gg, _ggb):
         (y,) = ctx.saved_tensors
-        return _MaskMul.apply(gg, y, ctx.act, ctx.c), None, None, None
+        return _MaskMul.apply(gg, y, ctx.act, ctx.c, False)[0], None, None, None, None
 
 
 class _Fwd(Function):
@@ -348,7 +353,12 @@ class _Fwd(Function):
         op = ctx.op
         gy = gy.contiguous()
         c = op.out_channels()
-        g = _MaskMul.apply(gy, y, ctx.act, c) if ctx.act != ACT_NONE else gy
+        want_b = ctx.has_bias and ctx.needs_input_grad[3]
+        gb_fused = None
+        if ctx.act != ACT_NONE:
+            g, gb_fused = _MaskMul.apply(gy, y, ctx.act, c, want_b)      # activation backward + bias column sums: one pass
+        else:
+            g = gy
         gx = _Tr.apply(op, g, w) if ctx.needs_input_grad[1] else None
         gw = None
         if ctx.needs_input_grad[2]:
@@ -359,9 +369,9 @@ class _Fwd(Function):
             else:
                 gw = _Wgrad.apply(op, x, g, w)
         gb = None
-        if ctx.has_bias and ctx.needs_input_grad[3]:
+        if want_b:
             # the bias gradient is never differentiated again on this path (the GP contributes exactly zero to biases)
-            gb = _bias_grad(g.detach(), c)
+            gb = gb_fused if gb_fused is not None else _bias_grad(g.detach(), c)
         return None, gx, gw, gb, None
 
 
