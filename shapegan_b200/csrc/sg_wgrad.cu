@@ -405,7 +405,7 @@ extern "C" int sg_wgrad_plan(sg_wgrad_args* a, size_t* workspace_bytes) {
   if (ksplit <= 0) {
     const int sms = sg_num_sms();
     const int base = p.m_tiles * p.n_groups;
-    ksplit = std::max(1, (sms + base - 1) / base);
+    ksplit = std::max(1, sms / base);                 // floor: all work items in ONE wave (a 2nd, mostly empty wave doubles the time)
     ksplit = std::min(ksplit, std::max(1, p.row_tiles));
     // keep the fp32 partial workspace modest (<= 256 MB)
     while (ksplit > 1 && (size_t)ksplit * p.m_pad * p.n_total * 4 > (256u << 20)) --ksplit;
