@@ -149,8 +149,9 @@ int sg_unary_bwd_f32(const float* gy, const float* y, float* gx, int64_t n, int 
 /* weight element of column k lives at w[(k / wc)*s_t + (k % wc)*s_c] (wc % 8 == 0) */
 int sg_rowdot_fwd(const void* x, int64_t x_ps, int planes, int64_t rows, int c, const float* w, int wc, int64_t s_t, int64_t s_c,
                   const float* bias, int act, float* y, void* stream);
+/* x_mask_act != SG_ACT_NONE additionally multiplies gx by act'(x) (x = stored activation feeding this layer) */
 int sg_rowdot_bwd(const float* gy, const float* y, int act, const void* x, int64_t x_ps, int planes, int64_t rows, int c,
-                  const float* w, int wc, int64_t s_t, int64_t s_c, void* gx, int64_t gx_ps, double* sums, void* stream);
+                  const float* w, int wc, int64_t s_t, int64_t s_c, void* gx, int64_t gx_ps, double* sums, int x_mask_act, void* stream);
 int sg_to_planes(const float* src, int64_t src_ld, int64_t rows, int c_src, void* dst, int64_t dst_ps, int planes, int c_dst,
                  void* stream);
 int sg_from_planes(const void* src, int64_t src_ps, int planes, int64_t rows, int c_src, int c_take, float* dst, int64_t dst_ld,

@@ -77,7 +77,7 @@ SYMBOLS = {
     'sg_unary_f32': 'pplip',
     'sg_unary_bwd_f32': 'ppplip',
     'sg_rowdot_fwd': 'plilipillpipp',
-    'sg_rowdot_bwd': 'ppiplilipillplpp',
+    'sg_rowdot_bwd': 'ppiplilipillplpip',
     'sg_to_planes': 'pllipliip',
     'sg_from_planes': 'pliliiplifp',
     'sg_sdf_pack_input': 'pppilpliip',

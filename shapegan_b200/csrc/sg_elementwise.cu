@@ -269,7 +269,7 @@ __global__ void sg_rowdot_fwd_block_kernel(const bf16* x, long long x_ps, int pl
 // g[r] = gy[r]*act'(y[r]);  gx[r,:] = g[r]*w (planes);  gw[c] += sum_r g[r]*x[r,c];  gb += sum_r g[r]
 __global__ void sg_rowdot_bwd_kernel(const float* gy, const float* y, int act, const bf16* x, long long x_ps, int planes,
                                      long long rows, int c, const float* w, int wc, long long s_t, long long s_c, bf16* gx,
-                                     long long gx_ps, double* sums, int P8, int R, long long rows_per_block) {
+                                     long long gx_ps, double* sums, int P8, int R, long long rows_per_block, int x_mask_act) {
   // blockIdx.y selects a slab of P8 piece columns (wide rows: C up to 16384)
   const int pl = threadIdx.x % P8, r = threadIdx.x / P8;
   const int p8 = blockIdx.y * P8 + pl;
@@ -283,8 +283,10 @@ __global__ void sg_rowdot_bwd_kernel(const float* gy, const float* y, int act, c
   for (long long row = r0 + r; row < r1; row += R) {
     const float g = gy[row] * act_grad_from_output(y[row], act);
     const long long off = row * c + p8 * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 1.f;
     if (x) {
-      float v[8];
       load8(x, x_ps, planes, off, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[0][j] += g * v[j];
@@ -293,7 +295,7 @@ __global__ void sg_rowdot_bwd_kernel(const float* gy, const float* y, int act, c
     if (gx) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = g * wv[j];
+      for (int j = 0; j < 8; ++j) o[j] = g * wv[j] * (x_mask_act != ACT_NONE ? act_grad_from_output(v[j], x_mask_act) : 1.f);
       store8(gx, gx_ps, planes, off, o);
     }
   }
@@ -686,7 +688,8 @@ extern "C" int sg_rowdot_fwd(const void* x, int64_t x_ps, int planes, int64_t ro
   return 0;
 }
 extern "C" int sg_rowdot_bwd(const float* gy, const float* y, int act, const void* x, int64_t x_ps, int planes, int64_t rows, int c,
-                             const float* w, int wc, int64_t s_t, int64_t s_c, void* gx, int64_t gx_ps, double* sums, void* stream) {
+                             const float* w, int wc, int64_t s_t, int64_t s_c, void* gx, int64_t gx_ps, double* sums, int x_mask_act,
+                             void* stream) {
   if (rows <= 0) return 0;
   if (wc <= 0) { wc = c; s_t = 0; s_c = 1; }
   // wide rows are processed in slabs of <= 2048 columns (grid.y); c must divide evenly into slabs
@@ -697,7 +700,7 @@ extern "C" int sg_rowdot_bwd(const float* gy, const float* y, int act, const voi
   if (rc) return rc;
   dim3 grid(k.grid, slabs);
   sg_rowdot_bwd_kernel<<<grid, k.block, k.smem, ST(stream)>>>(gy, y, act, (const bf16*)x, x_ps, planes, rows, c, w, wc, s_t, s_c,
-                                                            (bf16*)gx, gx_ps, sums, k.P8, k.R, k.rpb);
+                                                            (bf16*)gx, gx_ps, sums, k.P8, k.R, k.rpb, x_mask_act);
   SG_CUDA_CHECK_LAUNCH();
   return 0;
 }

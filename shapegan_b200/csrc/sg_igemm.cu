@@ -111,8 +111,8 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
     mbar_wait(&hdr->accfull[ab], aph, p.err);
     tc_fence_after();
     const bool tile_full = (nt * p.bn + p.bn <= p.n_valid);
-    const bool fast = tile_full && p.mask == nullptr && (p.bn & 31) == 0 &&
-                      ((p.out_kind == SG_OUT_BF16 && (p.out_ld & 7) == 0) || (p.out_kind == SG_OUT_F32 && (p.out_ld & 3) == 0));
+    const bool fast = tile_full && (p.bn & 31) == 0 &&
+                      ((p.out_kind == SG_OUT_BF16 && (p.out_ld & 7) == 0) || (p.out_kind == SG_OUT_F32 && (p.out_ld & 3) == 0 && p.mask == nullptr));
     for (int sub = 0; sub < p.mt; ++sub) {
       const long long gr = ((long long)mtile * p.mt + sub) * kTileRows + trow;
       const bool valid = gr < p.rows;
@@ -143,6 +143,17 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
           }
           if (p.out_kind == SG_OUT_BF16) {
             bf16* o = reinterpret_cast<bf16*>(p.out) + obase + c0;
+            if (p.mask != nullptr) {       // out *= act'(mask): the activation backward of the consumer layer, fused
+              const bf16* mk = p.mask + obase + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 m = __ldg(reinterpret_cast<const uint4*>(mk + j));
+                v[j] *= act_grad_from_output(bf16lo_to_f(m.x), p.mask_act); v[j + 1] *= act_grad_from_output(bf16hi_to_f(m.x), p.mask_act);
+                v[j + 2] *= act_grad_from_output(bf16lo_to_f(m.y), p.mask_act); v[j + 3] *= act_grad_from_output(bf16hi_to_f(m.y), p.mask_act);
+                v[j + 4] *= act_grad_from_output(bf16lo_to_f(m.z), p.mask_act); v[j + 5] *= act_grad_from_output(bf16hi_to_f(m.z), p.mask_act);
+                v[j + 6] *= act_grad_from_output(bf16lo_to_f(m.w), p.mask_act); v[j + 7] *= act_grad_from_output(bf16hi_to_f(m.w), p.mask_act);
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 hi;

@@ -256,12 +256,13 @@ def rowdot_fwd(x, c, w, bias, act, wc=0, s_t=0, s_c=1):
     return y
 
 
-def rowdot_bwd(gy, y, act, x, c, w, need_gx, need_gw, planes, rows, wc=0, s_t=0, s_c=1):
+def rowdot_bwd(gy, y, act, x, c, w, need_gx, need_gw, planes, rows, wc=0, s_t=0, s_c=1, x_mask_act=L.ACT_NONE):
     dev = gy.device
     gx = torch.empty((planes, rows, c), dtype=torch.bfloat16, device=dev) if need_gx else None
     sums = dsums(c + 8, dev) if need_gw else None
-    _call('sg_rowdot_bwd', _p(gy), _p(y), act, _p(x) if need_gw else None, _ps(x) if x is not None else 0, planes, rows, c, _p(w),
-          wc, s_t, s_c, _p(gx), _ps(gx), _p(sums))
+    use_x = need_gw or x_mask_act != L.ACT_NONE
+    _call('sg_rowdot_bwd', _p(gy), _p(y), act, _p(x) if use_x else None, _ps(x) if x is not None else 0, planes, rows, c, _p(w),
+          wc, s_t, s_c, _p(gx), _ps(gx), _p(sums), x_mask_act)
     return gx, sums
 
 
