@@ -150,24 +150,15 @@ class SDFNetFunction(Function):
         def f32(shape):
             return torch.empty(shape, dtype=torch.float32, device=dev)
 
-        # ---- head: Linear(256->1) + tanh; its input gradient comes out already multiplied by relu'(h7)
-        g, sums = raw.rowdot_bwd(gout, out, L.ACT_TANH, hs[6], HID, w[7], True, need_w[7] or need_b[7], planes, n, x_mask_act=L.ACT_RELU)
+        # ---- head: Linear(256->1) + tanh
+        gh, sums = raw.rowdot_bwd(gout, out, L.ACT_TANH, hs[6], HID, w[7], True, need_w[7] or need_b[7], planes, n)
         if need_w[7] or need_b[7]:
             gw[7] = raw.emit_sums(sums, f32(w[7].shape), HID)
             gb[7] = raw.emit_sums(sums[HID:], f32((1,)), 1)
         gx_a = gx_b = None
-
-        def dgrad(gin, wi, tag, mask):
-            """(gin . W) * relu'(mask): the activation backward of the layer below is fused into the dgrad epilogue"""
-            img = PACK_CACHE.get(wi, tag, planes, lambda t, pl: _pack_lin_t(t, pl, HID, HID))
-            o = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
-            raw.igemm(L.MODE_DENSE, planes, gin, (1, 1, 1, 1, HID), n, HID, img, HID, o, HID, mask=mask, mask_act=L.ACT_RELU)
-            return o
-
         for i in (6, 5, 4, 3, 2, 1, 0):
-            # g = dL/d(pre-activation of layer i) (already masked); bias gradient = its column sums (read-only pass)
+            g, sums = raw.act_bwd(gh, hs[i], L.ACT_RELU, HID, want_sums=need_b[i])
             if need_b[i]:
-                _, sums = raw.act_bwd(g, None, L.ACT_NONE, HID, want_sums=True, want_g=False)
                 gb[i] = raw.emit_sums(sums, f32((HID,)), HID)
             src = hs[i - 1] if i > 0 else x_in
             if i == 4:
@@ -180,7 +171,9 @@ class SDFNetFunction(Function):
                     img = PACK_CACHE.get(w[4], 'sdf_t4in', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8, col0=HID))
                     gx_b = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
                     raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, cin, gx_b, cin8, n_pad=raw.round_up(cin8, 16))
-                g = dgrad(g, w[4], 'sdf_t4h', hs[3])
+                img = PACK_CACHE.get(w[4], 'sdf_t4h', planes, lambda t, pl: _pack_lin_t(t, pl, HID, HID))
+                gh = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
+                raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, HID, gh, HID)
             elif i == 0:
                 if need_w[0]:
                     gw[0] = f32(w[0].shape)
@@ -193,7 +186,9 @@ class SDFNetFunction(Function):
                 if need_w[i]:
                     gw[i] = f32(w[i].shape)
                     raw.wgrad(L.MODE_DENSE, planes, g, HID, src, (1, 1, 1, 1, HID), n, gw[i], sm=HID, st=0, sc=1, m_valid=HID)
-                g = dgrad(g, w[i], 'sdf_t%d' % i, hs[i - 1])
+                img = PACK_CACHE.get(w[i], 'sdf_t%d' % i, planes, lambda t, pl: _pack_lin_t(t, pl, HID, HID))
+                gh = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
+                raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, HID, gh, HID)
         gpoints = glatent = None
         if need_points or need_latent:
             gpoints = f32((n, 3)) if need_points else None
