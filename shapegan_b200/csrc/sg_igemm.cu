@@ -610,7 +610,8 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   if (bn > 256 || (bn & 15) || a->n_pad % bn) return sg_fail(-20, "sg_igemm: bad bn");
   const int n_tiles = a->n_pad / bn;
   // two M sub-tiles share every B tile (halves the weight traffic out of L2) once there is more than one wave of work
-  if (mt <= 0) mt = (row_tiles * p.classes * n_tiles > sms && bn * 2 <= 512) ? 2 : 1;
+  // (not when that would cost the accumulator double buffer: with bn = 256 two sub-tiles fill TMEM and the epilogue serialises)
+  if (mt <= 0) mt = (row_tiles * p.classes * n_tiles > sms && bn * 4 <= 512) ? 2 : 1;
   if (mt < 1 || mt > 2 || mt * bn > 512) return sg_fail(-21, "sg_igemm: bad mt");
   if (ksplit <= 0) ksplit = 1;
   if (ksplit > p.kchunks) ksplit = p.kchunks;
