@@ -170,7 +170,7 @@ class SDFNetFunction(Function):
                 if need_points or need_latent:
                     img = PACK_CACHE.get(w[4], 'sdf_t4in', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8, col0=HID))
                     gx_b = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
-                    raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, cin, gx_b, cin8, n_pad=raw.round_up(cin8, 16))
+                    raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, cin8, gx_b, cin8, n_pad=cin8)   # rows >= cin of the image are zero
                 img = PACK_CACHE.get(w[4], 'sdf_t4h', planes, lambda t, pl: _pack_lin_t(t, pl, HID, HID))
                 gh = torch.empty((planes, n, HID), dtype=torch.bfloat16, device=dev)
                 raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, HID, gh, HID)
@@ -181,7 +181,7 @@ class SDFNetFunction(Function):
                 if need_points or need_latent:
                     img = PACK_CACHE.get(w[0], 'sdf_t0', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8))
                     gx_a = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
-                    raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, cin, gx_a, cin8, n_pad=raw.round_up(cin8, 16))
+                    raw.igemm(L.MODE_DENSE, planes, g, (1, 1, 1, 1, HID), n, HID, img, cin8, gx_a, cin8, n_pad=cin8)   # rows >= cin of the image are zero
             else:
                 if need_w[i]:
                     gw[i] = f32(w[i].shape)
