@@ -481,6 +481,32 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
   return 0;
 }
 
+// conv weights (taps = 64, grad index = m*sm + c*64 + tap): sum the splits and transpose (tap <-> c) through shared memory so that
+// both the partial reads (c contiguous) and the gradient writes (tap contiguous) are coalesced.  grid = (m_valid, cb/32).
+__global__ void sg_wgrad_reduce_t64_kernel(const sg_wgrad_reduce_args a) {
+  __shared__ float tile[32][65];
+  const int m = blockIdx.x, c0 = blockIdx.y * 32;
+  const long long n_total = 64LL * a.cb;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;          // 8 warps
+  for (int tap = wrp; tap < 64; tap += 8) {
+    float acc = 0.f;
+    const int c = c0 + lane;
+    if (c < a.cb) {
+      const float* p = a.partials + (size_t)m * n_total + (size_t)tap * a.cb + c;
+      for (int s = 0; s < a.ksplit; ++s) acc += p[(size_t)s * a.m_pad * n_total];
+    }
+    tile[lane][tap] = acc * a.scale;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+    const int c = i >> 6, tap = i & 63;
+    if (c0 + c < a.cb && (a.c_valid <= 0 || c0 + c < a.c_valid)) {
+      float* g = a.grad + (long long)m * a.sm + (long long)(c0 + c) * 64 + tap;
+      *g = a.accumulate ? (*g + tile[c][tap]) : tile[c][tap];
+    }
+  }
+}
+
 // many splits, few outputs (e.g. the 64x64 filter of Conv3d(1->64) reduced over 148 row splits): one warp per output element
 __global__ void sg_wgrad_reduce_warp_kernel(const sg_wgrad_reduce_args a) {
   const long long n_total = (long long)a.taps * a.cb;
@@ -509,6 +535,12 @@ extern "C" int sg_wgrad_reduce(const sg_wgrad_reduce_args* a, void* stream) {
   const long long total = (long long)a->m_valid * a->taps * a->cb;
   if (total <= 0) return 0;
   const int block = 256;
+  if (a->taps == 64 && a->st == 1 && a->sc == 64 && total > (1 << 16)) {
+    dim3 grid(a->m_valid, (a->cb + 31) / 32);
+    sg_wgrad_reduce_t64_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+    SG_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   if (a->ksplit >= 16 && total <= (1 << 16)) {
     const int grid = (int)std::min<long long>((total * 32 + block - 1) / block, 148 * 16);
     sg_wgrad_reduce_warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
