@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     const int lag = max(1, S - 2);
     int pending = 0, oldest = 0;
     const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+    const bool patch_fast = p.mode == SG_MODE_PATCH && (p.aW & 15) == 0;   // rows decoded inside patch_fill8's caller
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
       int cls, nt, mtile, ks;
       decode_work(p, w, cls, nt, mtile, ks);
@@ -335,22 +336,24 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           ri_n[sub][i] = -1; ri_c[sub][i] = 0;
-          if (sub < p.mt) {
+          if (sub < p.mt && !patch_fast) {
             long long gr = ((long long)mtile * p.mt + sub) * kTileRows + rb + 16 * i;
             if (gr < p.rows) {
               if (p.mode == SG_MODE_DENSE) {
                 ri_n[sub][i] = (int)gr;
               } else if (p.mode == SG_MODE_CONVT) {
-                int qw = (int)(gr % p.aW); long long t = gr / p.aW;
-                int qh = (int)(t % p.aH); t /= p.aH;
-                int qd = (int)(t % p.aD); int n = (int)(t / p.aD);
+                const uint32_t g32 = (uint32_t)gr;                                  // rows < 2^31 (host-checked)
+                int qw = (int)(g32 % (uint32_t)p.aW); uint32_t t = g32 / (uint32_t)p.aW;
+                int qh = (int)(t % (uint32_t)p.aH); t /= (uint32_t)p.aH;
+                int qd = (int)(t % (uint32_t)p.aD); int n = (int)(t / (uint32_t)p.aD);
                 ri_n[sub][i] = n * p.aD * p.aH * p.aW;
                 ri_c[sub][i] = (uint32_t)(qd + 1) | ((uint32_t)(qh + 1) << 10) | ((uint32_t)(qw + 1) << 20);
               } else {  // CONV / PATCH: rows enumerate the stride-2 output grid
                 const int oW = p.aW >> 1, oH = p.aH >> 1, oD = p.aD >> 1;
-                int ow = (int)(gr % oW); long long t = gr / oW;
-                int oh = (int)(t % oH); t /= oH;
-                int od = (int)(t % oD); int n = (int)(t / oD);
+                const uint32_t g32 = (uint32_t)gr;
+                int ow = (int)(g32 % (uint32_t)oW); uint32_t t = g32 / (uint32_t)oW;
+                int oh = (int)(t % (uint32_t)oH); t /= (uint32_t)oH;
+                int od = (int)(t % (uint32_t)oD); int n = (int)(t / (uint32_t)oD);
                 ri_n[sub][i] = n * p.aD * p.aH * p.aW;
                 ri_c[sub][i] = (uint32_t)(2 * od) | ((uint32_t)(2 * oh) << 10) | ((uint32_t)(2 * ow) << 20);  // (2o-1)+1
               }
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
         mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
         uint8_t* st = stage0 + (size_t)s * p.stage_bytes;
         const uint32_t a_base = smem_u32(st);
-        if (p.mode == SG_MODE_PATCH && (p.aW & 15) == 0) {
+        if (patch_fast) {
           // fast im2col: thread (rg = tid>>3, g) fills 8 consecutive output-x rows of piece g from two register-blocked lines
           const float* vol = reinterpret_cast<const float*>(p.a_ptr);
           const int oW = p.aW >> 1, oH = p.aH >> 1, oD = p.aD >> 1;
@@ -551,6 +554,7 @@ static int igemm_validate(const sg_igemm_args* a) {
   if (a->k <= 0 || (a->k & 63)) return sg_fail(-4, "sg_igemm: K must be a positive multiple of 64");
   if (a->n_pad <= 0 || (a->n_pad & 15) || a->n_valid <= 0 || a->n_valid > a->n_pad) return sg_fail(-5, "sg_igemm: bad N");
   if (a->rows < 0) return sg_fail(-6, "sg_igemm: negative rows");
+  if (a->mode != SG_MODE_DENSE && a->rows >= (1LL << 31)) return sg_fail(-6, "sg_igemm: conv rows must be < 2^31");
   if (!a->a.ptr || !a->b_packed || !a->out) return sg_fail(-7, "sg_igemm: null tensor");
   if (a->mode == SG_MODE_DENSE) {
     if (a->a.c & 7) return sg_fail(-8, "sg_igemm: DENSE needs C % 8 == 0");
