@@ -33,6 +33,12 @@ FLOPS_D2_FWD = 2 * 17179.9e6          # Conv3d(64->128,k4,s2,p1) forward at B=64
 STEP_GFLOP = {'wgan': 694.5, 'wgan_gp': 694.5 + 214.7}      # SURVEY.md 8d, as written, B=64
 
 
+def workload_name(wl, b):
+    if wl == 'autodecoder':
+        return 'configs[2]: DeepSDF autodecoder 16384 pts x 512 shapes/step (train_sdf_autodecoder.py:84-91)'
+    return 'configs[1]: 3D-CNN WGAN%s G+D step 32^3, batch %d/GPU (train_wgan.py:62-71 + :75-84)' % ('-GP' if wl == 'wgan_gp' else ' (clip)', b)
+
+
 def peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -119,8 +125,6 @@ def run_reference(args, rank, world):
         return
     from oracle import ref_steps as S
     from oracle import shapes as TS
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
     b = 8
     wl = args.workload
     if wl.startswith('wgan'):
@@ -146,6 +150,7 @@ def run_reference(args, rank, world):
         run = lambda: step(pts, sdf, idx)             # noqa: E731
         units, unit, metric = n, 'points/s', 'sdfnet_autodecoder_step_points_per_s'
         sample = '%d points x %d shapes of the 16384x512 step, fp32, torch CPU' % (n // shapes, shapes)
+    cores, calib = pick_cpu_threads(run)
     for _ in range(max(1, min(args.warmup, 2))):
         run()
     steps = max(1, min(args.steps, 5))
@@ -154,19 +159,54 @@ def run_reference(args, rank, world):
         run()
     dt = (time.perf_counter() - t0) / steps
     v = units / dt
+    sample += '; threads picked by a one-step sweep %s' % calib
     print(json.dumps({
         'impl': 'reference', 'metric': metric, 'value': v, 'unit': unit, 'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'note': 'oracle port of the reference step on host cores (reference is pure PyTorch; /root/reference cannot travel)'},
+        'config': {'workload': workload_name(args.workload, args.batch), 'global_batch': args.gpus * args.batch, 'parallelism': 'dp%d' % args.gpus,
+                   'note': 'oracle port of the reference step (oracle/ref_steps.py = the reference modules\' torch-CPU fp32 path) on host cores, '
+                           'bounded sample; the reference is pure PyTorch and /root/reference cannot travel to the GPU box'},
         'cpu_baseline': {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def usable_cpus():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:                                    # cgroup v2 quota of the container, if any
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def pick_cpu_threads(run):
+    """torch CPU thread count that runs the reference step fastest on this host: os.cpu_count() threads oversubscribe
+    the GPU boxes badly (128 logical CPUs, 22.9 s/step at 128 threads vs 1.5 s), so time one step at a few counts."""
+    avail = usable_cpus()
+    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail} | {min(avail, 8)})
+    torch.set_num_threads(cands[0])
+    run()                                   # warm-up (primitive caches, allocator)
+    best, log = None, []
+    for c in cands:
+        torch.set_num_threads(c)
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+        log.append('%d:%.2fs' % (c, dt))
+        if best is None or dt < best[1]:
+            best = (c, dt)
+    torch.set_num_threads(best[0])
+    return best[0], '{' + ' '.join(log) + '}'
 
 
 def cpu_baseline(workload):
     from oracle import ref_steps as S
     from oracle import shapes as TS
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
     b = 8
     gen = S.make_params(TS.gen_shapes(), 601)
     cri = S.make_params(TS.disc_shapes(), 602)
@@ -175,14 +215,14 @@ def cpu_baseline(workload):
     z1 = torch.randn((b, 128), generator=torch.Generator().manual_seed(1))
     z2 = torch.randn((b, 128), generator=torch.Generator().manual_seed(2))
     alpha = torch.rand((b, 1, 1, 1), generator=torch.Generator().manual_seed(3))
-    step(real, z1, z2, alpha)
+    cores, calib = pick_cpu_threads(lambda: step(real, z1, z2, alpha))
     n = 3
     t0 = time.perf_counter()
     for _ in range(n):
         step(real, z1, z2, alpha)
     dt = (time.perf_counter() - t0) / n
     return {'value': b * VOX / dt, 'unit': 'voxels/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d steps at B=%d of the B=64 G+D step (oracle/ref_steps.py, torch CPU fp32, %d threads)' % (n, b, cores)}
+            'sample': '%d steps at B=%d of the B=64 G+D step (oracle/ref_steps.py, torch CPU fp32, %d threads picked by a one-step sweep %s)' % (n, b, cores, calib)}
 
 
 # --------------------------------------------------------------------------------------------------------- roofline probe
@@ -336,7 +376,7 @@ def main():
         'metric': 'wgan_gd_step_voxels_per_s', 'value': world * b * VOX / (ms_step * 1e-3), 'unit': 'voxels/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'bf16x3(fp32x)', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: 3D-CNN WGAN%s G+D step 32^3, batch %d/GPU (train_wgan.py:62-71 + :75-84)' % ('-GP' if gp else ' (clip)', b),
+        'config': {'workload': workload_name(args.workload, b),
                    'global_batch': world * b, 'parallelism': 'dp%d' % world, 'launch': graph_note, 'l2': 'flushed (256 MiB memset) between timed iterations',
                    'step_gflop_as_written': STEP_GFLOP[args.workload] * b / 64.0,
                    'step_tflops': STEP_GFLOP[args.workload] * b / 64.0 / ms_step, 'step_frac_of_sustained_peak': STEP_GFLOP[args.workload] * b / 64.0 / ms_step / pk.get('bf16_tflops_sustained', 1400.0)},
@@ -384,7 +424,7 @@ def bench_autodecoder(args, rank, world, dev, lib):
     print(json.dumps({
         'metric': 'sdfnet_autodecoder_step_points_per_s', 'value': world * n / (ms * 1e-3), 'unit': 'points/s', 'n_gpus': world, 'steps': steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': 'configs[2]: DeepSDF autodecoder 16384 pts x 512 shapes/step (train_sdf_autodecoder.py:84-91)', 'points_per_gpu': n,
+        'config': {'workload': workload_name('autodecoder', 0), 'points_per_gpu': n,
                    'l2': 'inputs (%.1f GB) exceed L2' % (n * 20 / 1e9), 'parallelism': 'dp%d' % world},
         'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': tflops / pk['bf16_tflops_sustained'],
                      'traffic': None, 'note': 'whole step, 2.763 MFLOP/point fwd+bwd (SURVEY 8d); peak = ' + src + ' sustained'},

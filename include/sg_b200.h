@@ -197,6 +197,25 @@ typedef struct {
 int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream);
 int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32_t* aux_floats);
 
+/* Fused input-gradient chain of the same MLP (what autograd runs for SDFNet.forward, model/sdf_net.py:56-61, between the
+ * tanh head and layers1.0): g7 = gout*(1-out^2)*w8*[h7>0], then g_{l-1} = (g_l . W_l[:, :256]) * [h_{l-1}>0] for l = 7..2,
+ * one persistent CTA per tile pair.  hstash = the forward's stash; wt_img = 24 chunks of 32 KB = sg_pack_b images of the
+ * TRANSPOSED weights B[n = in-feature][k = out-feature] of layers2.4, layers2.2, layers2.0[:, :256], layers1.6, layers1.4,
+ * layers1.2 (in that order); w8 = layers2.6.weight [256].  gstash receives g_1..g_7 as bf16 [7][n][256] (index l-1): the
+ * operands of the weight-gradient GEMMs, bias sums and the two input-gradient GEMMs (sg_wgrad / sg_act_bwd / sg_igemm).
+ * Both fused kernels keep their small fp32 tables in __constant__ memory, uploaded on `stream` by the call itself: do not
+ * run two DIFFERENT SDFNets concurrently on two streams of one process. */
+typedef struct {
+  const float* gout; /* [n] gradient w.r.t. the tanh output */
+  const float* out;  /* [n] the forward's output */
+  const void* hstash;
+  const void* wt_img;
+  const float* w8;
+  int64_t n;
+  void* gstash;
+} sg_sdfnet_bwd_args;
+int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream);
+
 /* ---- misc ---- */
 int sg_abi_version(void);
 const char* sg_last_error(void);

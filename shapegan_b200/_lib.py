@@ -49,6 +49,11 @@ class SgSdfnetFwdArgs(ctypes.Structure):
                 ('aux', c_void_p), ('out', c_void_p), ('stash', c_void_p)]
 
 
+class SgSdfnetBwdArgs(ctypes.Structure):
+    _fields_ = [('gout', c_void_p), ('out', c_void_p), ('hstash', c_void_p), ('wt_img', c_void_p), ('w8', c_void_p),
+                ('n', c_int64), ('gstash', c_void_p)]
+
+
 # every symbol include/sg_b200.h declares, with (restype, argtypes); tests check that all of them resolve
 SYMBOLS = {
     'sg_abi_version': (c_int32, []),
@@ -65,6 +70,7 @@ SYMBOLS = {
     'sg_pack_b': (c_int32, [ctypes.POINTER(SgPackBArgs), c_void_p]),
     'sg_sdfnet_fwd': (c_int32, [ctypes.POINTER(SgSdfnetFwdArgs), c_void_p]),
     'sg_sdfnet_fwd_layout': (c_int32, [ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
+    'sg_sdfnet_bwd': (c_int32, [ctypes.POINTER(SgSdfnetBwdArgs), c_void_p]),
     # p = pointer, l = int64, i = int32, f = float (see _sig)
     'sg_act_bwd': 'plplpliliipp',
     'sg_bn_stats': 'plilipp',

@@ -1,16 +1,26 @@
-// Fused persistent DeepSDF MLP forward (model/sdf_net.py:56-61): all 8 layers of a pair of 128-point tiles inside one
-// CTA, bf16 operands / fp32 accumulation, activations never leave the SM.
+// Fused persistent DeepSDF MLP (model/sdf_net.py:56-61), bf16 operands / fp32 accumulation, activations never leave the SM.
 //
-//   TMEM  : two 128 x 256 fp32 accumulators (tile A: columns 0-255, tile B: 256-511)
+// FORWARD  sg_sdfnet_fwd_kernel: all 8 layers of a pair of 128-point tiles inside one CTA.
+//   TMEM  : two 128 x 256 fp32 accumulators (tile A: columns 0-255, tile B: 256-511).  Before the MMAs of a layer run, the
+//           epilogue warps PRE-LOAD the accumulator with that layer's fp32 bias (+ the K = 3 xyz columns of layers 1 and 5)
+//           through tcgen05.st, so every MMA accumulates and the epilogue is only  tcgen05.ld -> cvt.rn.relu.bf16x2 -> st.shared.
 //   SMEM  : hA, hB   64 KB each  hidden activations of the two tiles, K-major 128B-swizzled (4 chunks of [128][64] bf16),
 //                                 overwritten in place by the epilogue of every layer (it runs after the layer's MMAs retire)
 //           lat      32 KB       latent operand of ONE tile (2 chunks), gathered by index from the fp32 table
-//           w[2]     64 KB       two stages of streamed weights, one chunk = [256 n][64 k] bf16 = 32 KB, 28 chunks / pair:
-//                                 L1 latent(2) L2(4) L3(4) L4(4) L5 hidden(4) L5 latent(2) L6(4) L7(4); every chunk feeds BOTH tiles
+//           w[2]     64 KB       two stages of streamed weights, one chunk = [256 n][64 k] bf16 = 32 KB, 30 chunks / pair:
+//                                 L1 latent(2) L2(4) L3(4) L4(4) L5 latent(2, tile A) L5 hidden(4) L5 latent(2 again, tile B)
+//                                 L6(4) L7(4); the hidden chunks feed BOTH tiles
+//   CONST : biases, xyz columns, the 256 -> 1 head (14 KB, uploaded per launch): uniform reads that do not touch the
+//           2 KB of L1 this kernel's shared-memory carve-out leaves
 //   warps : 0 weight loader (1-D TMA bulk copies) | 1 MMA issuer (tcgen05.mma M128 N256 K16) | 4-7 latent gather |
-//           8-11 epilogue of tile A | 12-15 epilogue of tile B  (TMEM -> +bias/xyz -> ReLU -> bf16 -> SMEM [+ HBM stash])
-//   The xyz columns of layers 1 and 5 (K = 3) and all biases are applied in fp32 in the epilogue; layer 8 (256 -> 1) + tanh is a
-//   per-row dot product folded into the epilogue of layer 7.
+//           8-11 epilogue of tile A | 12-15 epilogue of tile B
+//   Layer 8 (256 -> 1) + tanh is a per-row dot product folded into the epilogue of layer 7.
+//
+// BACKWARD sg_sdfnet_bwd_kernel: the input-gradient chain g7 -> g6 -> ... -> g1 of a tile pair inside one CTA
+//   (g_l = gradient w.r.t. the pre-activation of layer l).  Head: g7 = gout (1 - out^2) w8 [h7 > 0]; layers 7..2:
+//   g_{l-1} = (g_l W_l[:, :256]) [h_{l-1} > 0] with g_l as the SMEM A operand, W_l^T streamed (24 chunks / pair, 3 stages),
+//   the ReLU mask read from the forward stash as 1 bit per element while the MMAs run.  Every g_l is written to `gstash`
+//   (bf16 [7][n][256]) for the weight-gradient GEMMs, the bias sums and the two input-gradient GEMMs that follow.
 #include <algorithm>
 #include <cstring>
 
@@ -20,7 +30,8 @@
 namespace sg {
 
 constexpr int kSdfThreads = 512;
-constexpr int kSdfChunks = 28;
+constexpr int kSdfImgChunks = 28;       // chunks in the weight image
+constexpr int kSdfStreamChunks = 30;    // chunks streamed per tile pair (the 2 latent chunks of layers2.0 twice)
 constexpr uint32_t kChunkBytes = 32768;
 constexpr uint32_t kSdfHdr = 2048;
 constexpr uint32_t kOffHA = kSdfHdr;
@@ -30,7 +41,7 @@ constexpr uint32_t kOffW = kOffLat + 32768;
 constexpr uint32_t kSdfSmem = kOffW + 2 * kChunkBytes;      // 231424 B
 
 struct SdfHdr {
-  uint64_t w_full[2], w_empty[2];
+  uint64_t w_full[3], w_empty[3];
   uint64_t lat_full, lat_empty;
   uint64_t acc_full[2], h_ready[2];
   uint32_t tmem_base;
@@ -38,7 +49,7 @@ struct SdfHdr {
 
 struct SdfP {
   const float* points; const float* latent; const int* index; long long n;
-  const char* w_img; const float* aux; float* out; bf16* stash;
+  const char* w_img; float* out; bf16* stash;
   long long pairs;
   int* err;
 };
@@ -49,6 +60,27 @@ constexpr int kAuxXb5 = 1024;       // float4[256] of layers2.0
 constexpr int kAuxBias = 2048;      // [5][256]: layers1.2, 1.4, 1.6, layers2.2, 2.4
 constexpr int kAuxW8 = 2048 + 5 * 256;
 constexpr int kAuxB8 = kAuxW8 + 256;
+constexpr int kAuxFloats = kAuxB8 + 1;
+
+__constant__ float c_sdf_aux[kAuxFloats];     // forward: see above; uploaded (device -> device) by sg_sdfnet_fwd on its stream
+__constant__ float c_sdf_w8[256];             // backward: layers2.6 weight row
+
+// fp32 value the accumulator of layer `l` starts from, columns [c0, c0+32) of the row at (px, py, pz)
+__device__ __forceinline__ void sdf_acc_init(int l, int c0, float px, float py, float pz, uint32_t (&v)[32]) {
+  if (l == 1 || l == 5) {
+    const float4* xb = reinterpret_cast<const float4*>(c_sdf_aux + (l == 1 ? kAuxXb1 : kAuxXb5)) + c0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float4 w = xb[j];
+      v[j] = __float_as_uint(fmaf(w.x, px, fmaf(w.y, py, fmaf(w.z, pz, w.w))));
+    }
+  } else {
+    const int bslot = (l < 5) ? l - 2 : l - 3;            // layers 2,3,4 -> 0,1,2 ; layers 6,7 -> 3,4
+    const float* b = c_sdf_aux + kAuxBias + bslot * 256 + c0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(b[j]);
+  }
+}
 
 __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __grid_constant__ SdfP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -78,49 +110,63 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
     if (lane == 0) {
       uint32_t g = 0;
       for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
-        for (int j = 0; j < kSdfChunks; ++j, ++g) {
+        for (int j = 0; j < kSdfStreamChunks; ++j, ++g) {
+          // stream position -> image chunk: [14,16) and [20,22) are the latent chunks 18,19 of layers2.0, [16,20) its hidden chunks 14-17
+          const int ic = j < 14 ? j : (j < 16 ? j + 4 : j - 2);
           const uint32_t st = g & 1u;
           mbar_wait(&hdr->w_empty[st], ((g >> 1) & 1u) ^ 1u, p.err);
           mbar_arrive_expect_tx(&hdr->w_full[st], kChunkBytes);
-          bulk_g2s(s_base + kOffW + st * kChunkBytes, p.w_img + (size_t)j * kChunkBytes, kChunkBytes, &hdr->w_full[st]);
+          bulk_g2s(s_base + kOffW + st * kChunkBytes, p.w_img + (size_t)ic * kChunkBytes, kChunkBytes, &hdr->w_full[st]);
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
+    // ================================================================ MMA issuer (every MMA accumulates: the epilogue warps
+    // pre-load the accumulators with the bias terms before they arrive on h_ready)
     const uint32_t idesc = umma_idesc(128, 256, false, false);
     uint32_t g = 0, lat_n = 0, hr_n[2] = {0, 0};
-    bool first = true;
-    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
-      // ---------- layer 1: latent part (2 resident weight chunks, one tile after the other through the shared latent tile)
-      if (!first) {
-        for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }   // accumulators drained
+    // latent part of a layer for tile t: 2 resident weight chunks (stages g, g+1) x the shared latent tile
+    auto latent_mma = [&](int t, bool commit_acc) {
+      mbar_wait(&hdr->lat_full, lat_n & 1u, p.err); ++lat_n;
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d = tmem_base + (uint32_t)t * 256u;
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t a = s_base + kOffLat + c * kTileBytes, b = s_base + kOffW + ((g + c) & 1u) * kChunkBytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, 1u);
+        }
+        umma_commit(&hdr->lat_empty);
+        if (commit_acc) umma_commit(&hdr->acc_full[t]);
       }
-      first = false;
+      __syncwarp();
+    };
+    auto wait_two_chunks = [&]() {
       mbar_wait(&hdr->w_full[g & 1u], (g >> 1) & 1u, p.err);
       mbar_wait(&hdr->w_full[(g + 1) & 1u], ((g + 1) >> 1) & 1u, p.err);
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(&hdr->lat_full, lat_n & 1u, p.err); ++lat_n;
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t d = tmem_base + (uint32_t)t * 256u;
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t a = s_base + kOffLat + c * kTileBytes, b = s_base + kOffW + ((g + c) & 1u) * kChunkBytes;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, (c | kk) ? 1u : 0u);
-          }
-          umma_commit(&hdr->lat_empty);
-          umma_commit(&hdr->acc_full[t]);
-        }
-        __syncwarp();
-      }
+    };
+    auto release_two_chunks = [&]() {
       if (lane == 0) { umma_commit(&hdr->w_empty[g & 1u]); umma_commit(&hdr->w_empty[(g + 1) & 1u]); }
       __syncwarp();
       g += 2;
-      // ---------- layers 2..7
-      for (int l = 2; l <= 7; ++l) {
-        for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }     // h[t] = activations of layer l-1
+    };
+    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+      for (int l = 1; l <= 7; ++l) {
+        // h[t] holds the activations of layer l-1 and accumulator t is drained and re-initialised
+        for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }
         tc_fence_after();
+        if (l == 1) {
+          wait_two_chunks();
+          latent_mma(0, true);
+          latent_mma(1, true);
+          release_two_chunks();
+          continue;
+        }
+        if (l == 5) {   // latent part of layers2.0 for tile A first: tile B's latent rows are gathered under the hidden chunks
+          wait_two_chunks();
+          latent_mma(0, false);
+          release_two_chunks();
+        }
         for (int c = 0; c < 4; ++c, ++g) {
           mbar_wait(&hdr->w_full[g & 1u], (g >> 1) & 1u, p.err);
           tc_fence_after();
@@ -130,34 +176,17 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
               const uint32_t d = tmem_base + (uint32_t)t * 256u;
               const uint32_t a = s_base + (t ? kOffHB : kOffHA) + c * kTileBytes;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, (c | kk) ? 1u : 0u);
-              if (c == 3 && l != 5) umma_commit(&hdr->acc_full[t]);
+              for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, 1u);
+              if (c == 3 && (l != 5 || t == 0)) umma_commit(&hdr->acc_full[t]);
             }
             umma_commit(&hdr->w_empty[g & 1u]);
           }
           __syncwarp();
         }
-        if (l == 5) {   // + latent part of layers2.0 on top of the hidden part
-          mbar_wait(&hdr->w_full[g & 1u], (g >> 1) & 1u, p.err);
-          mbar_wait(&hdr->w_full[(g + 1) & 1u], ((g + 1) >> 1) & 1u, p.err);
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&hdr->lat_full, lat_n & 1u, p.err); ++lat_n;
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t d = tmem_base + (uint32_t)t * 256u;
-              for (int c = 0; c < 2; ++c) {
-                const uint32_t a = s_base + kOffLat + c * kTileBytes, b = s_base + kOffW + ((g + c) & 1u) * kChunkBytes;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, 1u);
-              }
-              umma_commit(&hdr->lat_empty);
-              umma_commit(&hdr->acc_full[t]);
-            }
-            __syncwarp();
-          }
-          if (lane == 0) { umma_commit(&hdr->w_empty[g & 1u]); umma_commit(&hdr->w_empty[(g + 1) & 1u]); }
-          __syncwarp();
-          g += 2;
+        if (l == 5) {
+          wait_two_chunks();
+          latent_mma(1, true);
+          release_two_chunks();
         }
       }
     }
@@ -170,7 +199,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         const long long tile = pr * 2 + (u & 1);
         if (use > 0) mbar_wait(&hdr->lat_empty, (use - 1) & 1u, p.err);
         const int chunk = lane >> 4, piece = (lane & 15) >> 1, half = lane & 1;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const int r = gw * 32 + i;
           const long long gr = tile * kTileRows + r;
@@ -194,52 +223,49 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
     const int r = q * 32 + lane;
     uint8_t* hbuf = smem + (t ? kOffHB : kOffHA);
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
-    const float4* xb1 = reinterpret_cast<const float4*>(p.aux + kAuxXb1);
-    const float4* xb5 = reinterpret_cast<const float4*>(p.aux + kAuxXb5);
-    const float4* w8 = reinterpret_cast<const float4*>(p.aux + kAuxW8);
-    const float b8 = __ldg(p.aux + kAuxB8);
     uint32_t af_n = 0;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    {
+      const long long gr = ((long long)blockIdx.x * 2 + t) * kTileRows + r;
+      if (blockIdx.x < p.pairs && gr < p.n) { px = __ldg(p.points + gr * 3); py = __ldg(p.points + gr * 3 + 1); pz = __ldg(p.points + gr * 3 + 2); }
+      // accumulator of layer 1 of the first pair
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t iv[32];
+        sdf_acc_init(1, c0, px, py, pz, iv);
+        tmem_st32(t_addr + c0, iv);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&hdr->h_ready[t]);
+    }
     for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
       const long long gr = (pr * 2 + t) * kTileRows + r;
       const bool valid = gr < p.n;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (valid) { px = __ldg(p.points + gr * 3); py = __ldg(p.points + gr * 3 + 1); pz = __ldg(p.points + gr * 3 + 2); }
+      // points of this CTA's next pair (its layer-1 accumulator is initialised at the end of this pair)
+      const long long npr = pr + gridDim.x;
+      const long long ngr = (npr * 2 + t) * kTileRows + r;
+      float nx = 0.f, ny = 0.f, nz = 0.f;
+      if (npr < p.pairs && ngr < p.n) { nx = __ldg(p.points + ngr * 3); ny = __ldg(p.points + ngr * 3 + 1); nz = __ldg(p.points + ngr * 3 + 2); }
       for (int l = 1; l <= 7; ++l) {
         mbar_wait(&hdr->acc_full[t], af_n & 1u, p.err); ++af_n;
         tc_fence_after();
-        const bool xyz = (l == 1 || l == 5);
-        const float4* xb = (l == 1) ? xb1 : xb5;
-        const int bslot = (l < 5) ? l - 2 : l - 3;            // layers 2,3,4 -> 0,1,2 ; layers 6,7 -> 3,4
-        const float4* bias = reinterpret_cast<const float4*>(p.aux + kAuxBias + bslot * 256);
+        const int nl = (l < 7) ? l + 1 : 1;                        // layer whose accumulator start value goes in behind the drain
+        const bool init_next = (l < 7) || (npr < p.pairs);
+        const float ix = (l < 7) ? px : nx, iy = (l < 7) ? py : ny, iz = (l < 7) ? pz : nz;
         float dot = 0.f;
         bf16* srow = (p.stash != nullptr && valid) ? p.stash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 256 : nullptr;
+#pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
           uint32_t acc[32];
-          __syncwarp();
           tmem_ld32(t_addr + c0, acc);
           tmem_ld_wait();
-          float v[32];
-          if (xyz) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float4 w = __ldg(xb + c0 + j);
-              v[j] = fmaxf(__uint_as_float(acc[j]) + w.w + w.x * px + w.y * py + w.z * pz, 0.f);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(bias + ((c0 + j) >> 2));
-              v[j] = fmaxf(__uint_as_float(acc[j]) + b.x, 0.f);
-              v[j + 1] = fmaxf(__uint_as_float(acc[j + 1]) + b.y, 0.f);
-              v[j + 2] = fmaxf(__uint_as_float(acc[j + 2]) + b.z, 0.f);
-              v[j + 3] = fmaxf(__uint_as_float(acc[j + 3]) + b.w, 0.f);
-            }
-          }
           uint4 pk[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            pk[u].x = pack_bf16x2(v[u * 8], v[u * 8 + 1]); pk[u].y = pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]);
-            pk[u].z = pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]); pk[u].w = pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]);
+            pk[u].x = pack_relu_bf16x2(__uint_as_float(acc[u * 8]), __uint_as_float(acc[u * 8 + 1]));
+            pk[u].y = pack_relu_bf16x2(__uint_as_float(acc[u * 8 + 2]), __uint_as_float(acc[u * 8 + 3]));
+            pk[u].z = pack_relu_bf16x2(__uint_as_float(acc[u * 8 + 4]), __uint_as_float(acc[u * 8 + 5]));
+            pk[u].w = pack_relu_bf16x2(__uint_as_float(acc[u * 8 + 6]), __uint_as_float(acc[u * 8 + 7]));
           }
           if (l < 7) {
             const uint32_t chunk = (uint32_t)c0 >> 6, pbase = ((uint32_t)c0 & 63u) >> 3;
@@ -247,21 +273,226 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
             for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
           } else {
             // layers2.6 (256 -> 1) on the bf16-rounded activations (what the backward sees in the stash)
+            const float* w8 = c_sdf_aux + kAuxW8 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 w = __ldg(w8 + ((c0 + j) >> 2));
-              dot += bf16_round(v[j]) * w.x + bf16_round(v[j + 1]) * w.y + bf16_round(v[j + 2]) * w.z + bf16_round(v[j + 3]) * w.w;
+            for (int u = 0; u < 4; ++u) {
+              dot = fmaf(bf16lo_to_f(pk[u].x), w8[u * 8], dot); dot = fmaf(bf16hi_to_f(pk[u].x), w8[u * 8 + 1], dot);
+              dot = fmaf(bf16lo_to_f(pk[u].y), w8[u * 8 + 2], dot); dot = fmaf(bf16hi_to_f(pk[u].y), w8[u * 8 + 3], dot);
+              dot = fmaf(bf16lo_to_f(pk[u].z), w8[u * 8 + 4], dot); dot = fmaf(bf16hi_to_f(pk[u].z), w8[u * 8 + 5], dot);
+              dot = fmaf(bf16lo_to_f(pk[u].w), w8[u * 8 + 6], dot); dot = fmaf(bf16hi_to_f(pk[u].w), w8[u * 8 + 7], dot);
             }
           }
-          if (srow) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(srow + c0 + u * 8) = pk[u];
+          if (srow) { stg_256(srow + c0, pk[0], pk[1]); stg_256(srow + c0 + 16, pk[2], pk[3]); }
+          if (init_next) {
+            uint32_t iv[32];
+            sdf_acc_init(nl, c0, ix, iy, iz, iv);
+            tmem_st32(t_addr + c0, iv);
           }
         }
-        if (l == 7 && valid) p.out[gr] = tanhf(dot + b8);
+        if (l == 7 && valid) p.out[gr] = tanhf(dot + c_sdf_aux[kAuxB8]);
+        tmem_st_wait();
         if (l < 7) fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
         tc_fence_before();
         mbar_arrive(&hdr->h_ready[t]);
+      }
+      px = nx; py = ny; pz = nz;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------------------ backward
+constexpr int kSdfBwdThreads = 384;     // 0 weight loader | 1 MMA issuer | 4-7 epilogue of tile A | 8-11 epilogue of tile B
+constexpr int kSdfBwdChunks = 24;       // W7^T, W6^T, W5[:, :256]^T, W4^T, W3^T, W2^T, 4 chunks each
+constexpr int kSdfBwdStages = 3;
+constexpr uint32_t kOffBW = kOffHB + 65536;
+constexpr uint32_t kSdfBwdSmem = kOffBW + kSdfBwdStages * kChunkBytes;      // 231424 B
+
+struct SdfBwdP {
+  const float* gout; const float* out; const bf16* hstash; const char* wt_img; bf16* gstash;
+  long long n, pairs;
+  int* err;
+};
+
+__global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const __grid_constant__ SdfBwdP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  SdfHdr* hdr = reinterpret_cast<SdfHdr*>(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kSdfBwdStages; ++i) { mbar_init(&hdr->w_full[i], 1); mbar_init(&hdr->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hdr->acc_full[i], 1); mbar_init(&hdr->h_ready[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&hdr->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0) atomicExch(p.err, kErrSmemAlign);
+    __trap();
+  }
+  const uint32_t s_base = smem_u32(smem);
+
+  if (warp == 0) {
+    // ================================================================ weight loader
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+        for (int j = 0; j < kSdfBwdChunks; ++j) {
+          mbar_wait(&hdr->w_empty[st], ph ^ 1u, p.err);
+          mbar_arrive_expect_tx(&hdr->w_full[st], kChunkBytes);
+          bulk_g2s(s_base + kOffBW + st * kChunkBytes, p.wt_img + (size_t)j * kChunkBytes, kChunkBytes, &hdr->w_full[st]);
+          if (++st == kSdfBwdStages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc = umma_idesc(128, 256, false, false);
+    uint32_t st = 0, ph = 0, hr_n[2] = {0, 0};
+    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+      for (int l = 7; l >= 2; --l) {
+        for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }   // g_l in SMEM, accumulator drained
+        tc_fence_after();
+        for (int c = 0; c < 4; ++c) {
+          mbar_wait(&hdr->w_full[st], ph, p.err);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t b = s_base + kOffBW + st * kChunkBytes;
+            for (int t = 0; t < 2; ++t) {
+              const uint32_t d = tmem_base + (uint32_t)t * 256u;
+              const uint32_t a = s_base + (t ? kOffHB : kOffHA) + c * kTileBytes;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, (c | kk) ? 1u : 0u);
+              if (c == 3) umma_commit(&hdr->acc_full[t]);
+            }
+            umma_commit(&hdr->w_empty[st]);
+          }
+          __syncwarp();
+          if (++st == kSdfBwdStages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue of tile t
+    const int t = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint8_t* hbuf = smem + (t ? kOffHB : kOffHA);
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    uint32_t af_n = 0;
+    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+      const long long gr = (pr * 2 + t) * kTileRows + r;
+      const bool valid = gr < p.n;
+      // ---------- head: g7 = gout * tanh'(out) * w8 where h7 > 0 (model/sdf_net.py:50-51)
+      {
+        float s = 0.f;
+        if (valid) { const float o = __ldg(p.out + gr); s = __ldg(p.gout + gr) * (1.f - o * o); }
+        const bf16* hrow = p.hstash + ((size_t)6 * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
+        bf16* grow = p.gstash + ((size_t)6 * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
+#pragma unroll 2
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          u32x8 hv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (valid) hv[u] = ldg_nc_256(hrow + c0 + u * 16);
+            else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) hv[u].v[k] = 0u;
+            }
+          }
+          const float* w8 = c_sdf_w8 + c0;
+          uint32_t o[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const uint32_t hw = hv[k >> 3].v[k & 7];
+            const float lo = (hw & 0x7fffu) ? s * w8[2 * k] : 0.f;
+            const float hi = (hw & 0x7fff0000u) ? s * w8[2 * k + 1] : 0.f;
+            o[k] = pack_bf16x2(lo, hi);
+          }
+          uint4 pk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pk[u] = make_uint4(o[u * 4], o[u * 4 + 1], o[u * 4 + 2], o[u * 4 + 3]);
+          const uint32_t chunk = (uint32_t)c0 >> 6, pbase = ((uint32_t)c0 & 63u) >> 3;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
+          if (valid) { stg_256(grow + c0, pk[0], pk[1]); stg_256(grow + c0 + 16, pk[2], pk[3]); }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&hdr->h_ready[t]);
+      }
+      // ---------- layers 7..2: g_{l-1} = (g_l W_l) [h_{l-1} > 0]
+      for (int l = 7; l >= 2; --l) {
+        // ReLU mask of h_{l-1}, one bit per column of this thread's row, fetched while the MMAs of this layer run
+        uint32_t mb[8];
+        {
+          const bf16* hrow = p.hstash + ((size_t)(l - 2) * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {       // two rounds of 8 x 32-byte loads: 64 registers in flight, not 128
+            u32x8 hv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (valid) hv[i] = ldg_nc_256(hrow + half * 128 + i * 16);
+              else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hv[i].v[k] = 0u;
+              }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const uint32_t hw = hv[cc * 2 + (k >> 3)].v[k & 7];
+                bits |= ((hw & 0x7fffu) ? 1u : 0u) << (2 * k);
+                bits |= ((hw & 0x7fff0000u) ? 1u : 0u) << (2 * k + 1);
+              }
+              asm volatile("" : "+r"(bits));           // keeps the extraction of this round ahead of the next round's loads
+              mb[half * 4 + cc] = bits;
+            }
+          }
+        }
+        mbar_wait(&hdr->acc_full[t], af_n & 1u, p.err); ++af_n;
+        tc_fence_after();
+        bf16* grow = p.gstash + ((size_t)(l - 2) * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int c0 = c * 32;
+          uint32_t acc[32];
+          tmem_ld32(t_addr + c0, acc);
+          tmem_ld_wait();
+          const uint32_t bits = mb[c];
+          uint4 pk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = u * 8 + 2 * k;
+              const float lo = ((bits >> e) & 1u) ? __uint_as_float(acc[e]) : 0.f;
+              const float hi = ((bits >> (e + 1)) & 1u) ? __uint_as_float(acc[e + 1]) : 0.f;
+              o[k] = pack_bf16x2(lo, hi);
+            }
+            pk[u] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          if (l > 2) {
+            const uint32_t chunk = (uint32_t)c0 >> 6, pbase = ((uint32_t)c0 & 63u) >> 3;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
+          }
+          if (valid) { stg_256(grow + c0, pk[0], pk[1]); stg_256(grow + c0 + 16, pk[2], pk[3]); }
+        }
+        if (l > 2) {
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(&hdr->h_ready[t]);
+        } else {
+          tc_fence_before();      // orders the accumulator reads before the head of the next pair arrives on h_ready
+        }
       }
     }
   }
@@ -280,7 +511,7 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   SdfP p;
   memset(&p, 0, sizeof(p));
   p.points = a->points; p.latent = a->latent; p.index = a->index; p.n = a->n;
-  p.w_img = (const char*)a->w_img; p.aux = a->aux; p.out = a->out; p.stash = (bf16*)a->stash;
+  p.w_img = (const char*)a->w_img; p.out = a->out; p.stash = (bf16*)a->stash;
   const long long tiles = (a->n + kTileRows - 1) / kTileRows;
   p.pairs = (tiles + 1) / 2;
   p.err = sg_error_word();
@@ -290,6 +521,9 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
+  // biases / xyz columns / head -> constant bank (stream ordered, capturable; one SDFNet per stream at a time)
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_aux, a->aux, sizeof(float) * kAuxFloats, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
   const int grid = (int)std::min<long long>(p.pairs, sg_num_sms());
   sg_sdfnet_fwd_kernel<<<grid, kSdfThreads, kSdfSmem, (cudaStream_t)stream>>>(p);
   SG_CUDA_CHECK_LAUNCH();
@@ -297,8 +531,32 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
 }
 
 extern "C" int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32_t* aux_floats) {
-  if (chunks) *chunks = kSdfChunks;
+  if (chunks) *chunks = kSdfImgChunks;
   if (chunk_bytes) *chunk_bytes = (int32_t)kChunkBytes;
-  if (aux_floats) *aux_floats = kAuxB8 + 1;
+  if (aux_floats) *aux_floats = kAuxFloats;
+  return 0;
+}
+
+extern "C" int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream) {
+  if (!a || !a->gout || !a->out || !a->hstash || !a->wt_img || !a->w8 || !a->gstash) return sg_fail(-1, "sg_sdfnet_bwd: null");
+  if (a->n <= 0) return 0;
+  SdfBwdP p;
+  memset(&p, 0, sizeof(p));
+  p.gout = a->gout; p.out = a->out; p.hstash = (const bf16*)a->hstash; p.wt_img = (const char*)a->wt_img; p.gstash = (bf16*)a->gstash;
+  p.n = a->n;
+  const long long tiles = (a->n + kTileRows - 1) / kTileRows;
+  p.pairs = (tiles + 1) / 2;
+  p.err = sg_error_word();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfBwdSmem);
+    if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_w8, a->w8, sizeof(float) * 256, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+  const int grid = (int)std::min<long long>(p.pairs, sg_num_sms());
+  sg_sdfnet_bwd_kernel<<<grid, kSdfBwdThreads, kSdfBwdSmem, (cudaStream_t)stream>>>(p);
+  SG_CUDA_CHECK_LAUNCH();
   return 0;
 }

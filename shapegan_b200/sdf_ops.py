@@ -94,11 +94,12 @@ class SDFNetFunction(Function):
             out = raw.sdfnet_fwd(points, latent, index, img, aux, stash)
             if need_graph:
                 x_in = raw.sdf_pack_input(points, latent, index, lat, planes, cin8)
-                hs = [stash[i].unsqueeze(0) for i in range(7)]
                 ctx.meta = (planes, n, lat, cin, cin8, index is not None, latent.shape[0])
                 ctx.w_objs = w
-                ctx.save_for_backward(x_in, out, index if index is not None else torch.empty(0, device=dev), *hs, *w)
+                ctx.fused = True
+                ctx.save_for_backward(x_in, out, index if index is not None else torch.empty(0, device=dev), stash, *w)
             return out
+        ctx.fused = False
         x_in = raw.sdf_pack_input(points, latent, index, lat, planes, cin8)
         hs = []
         h = x_in
@@ -136,8 +137,9 @@ class SDFNetFunction(Function):
         planes, n, lat, cin, cin8, indexed, lat_rows = ctx.meta
         saved = ctx.saved_tensors
         x_in, out, index = saved[0], saved[1], saved[2]
-        hs = list(saved[3:10])
-        w = ctx.w_objs                       # saved[10:18] were version-checked by autograd
+        hstash = saved[3] if ctx.fused else None                                   # the fused forward's [7, n, 256] stash
+        hs = [hstash[i].unsqueeze(0) for i in range(7)] if ctx.fused else list(saved[3:10])
+        w = ctx.w_objs                       # the saved parameter tensors were version-checked by autograd
         dev = gout.device
         need_points = ctx.needs_input_grad[0]
         need_latent = ctx.needs_input_grad[1]
@@ -149,6 +151,10 @@ class SDFNetFunction(Function):
 
         def f32(shape):
             return torch.empty(shape, dtype=torch.float32, device=dev)
+
+        if ctx.fused and fused_bwd_enabled():
+            return _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, hstash, hs, w, gout,
+                                   need_points, need_latent, need_w, need_b)
 
         # ---- head: Linear(256->1) + tanh
         gh, sums = raw.rowdot_bwd(gout, out, L.ACT_TANH, hs[6], HID, w[7], True, need_w[7] or need_b[7], planes, n)
@@ -200,6 +206,81 @@ class SDFNetFunction(Function):
             grads.append(gw[i])
             grads.append(gb[i])
         return tuple(grads)
+
+
+def fused_bwd_enabled():
+    import os
+    return os.environ.get('SG_B200_NO_FUSED_SDF_BWD') != '1'
+
+
+def _fused_pack_t(w):
+    """24 transposed weight chunks in the stream order of sg_sdfnet_bwd_kernel: layers2.4, 2.2, 2.0[:, :256], layers1.6, 1.4, 1.2."""
+    uid = PACK_CACHE._uid(w[1])
+    order = (6, 5, 4, 3, 2, 1)
+    sig = tuple((w[i]._version, w[i].data_ptr()) for i in order)
+    hit = _FUSED_CACHE.get(('t', uid))
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    chunk = 32768
+    img = torch.empty(24 * chunk, dtype=torch.uint8, device=w[1].device)
+    for j, i in enumerate(order):
+        t = w[i].detach()
+        # B[n = in-feature][k = out-feature] = W[k, n]  (first 256 in-features: layers2.0 keeps its xyz/latent columns out)
+        raw.pack_b(t, 1, HID, HID, 1, HID, HID, s_n0=1, s_tap=0, s_c=t.stride(0), n_pad=HID, out=img[j * 4 * chunk:(j + 1) * 4 * chunk])
+    if not torch.cuda.is_current_stream_capturing():
+        _FUSED_CACHE[('t', uid)] = (sig, img)
+    return img
+
+
+def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, hstash, hs, w, gout, need_points, need_latent, need_w,
+                    need_b):
+    """Backward of the fused forward: ONE persistent kernel runs the whole input-gradient chain (sg_sdfnet_bwd) and leaves
+    g_1..g_7 in a bf16 stash; the weight gradients, bias sums and the two input-gradient GEMMs read that stash."""
+    dev = gout.device
+
+    def f32(shape):
+        return torch.empty(shape, dtype=torch.float32, device=dev)
+
+    gw = [None] * 8
+    gb = [None] * 8
+    assert hstash.shape == (7, n, HID) and hstash.is_contiguous()
+    if need_w[7] or need_b[7]:
+        _, sums = raw.rowdot_bwd(gout, out, L.ACT_TANH, hs[6], HID, w[7], False, True, planes, n)
+        gw[7] = raw.emit_sums(sums, f32(w[7].shape), HID)
+        gb[7] = raw.emit_sums(sums[HID:], f32((1,)), 1)
+    gst = raw.sdfnet_bwd(gout, out, hstash, _fused_pack_t(w), w[7].detach().reshape(-1))
+    g = [gst[i].unsqueeze(0) for i in range(7)]                                     # g[i]: gradient w.r.t. the pre-activation of layer i+1
+    for i in range(7):
+        if need_b[i]:
+            _, sums = raw.act_bwd(g[i], None, L.ACT_NONE, HID, want_sums=True, want_g=False)
+            gb[i] = raw.emit_sums(sums, f32((HID,)), HID)
+        if not need_w[i]:
+            continue
+        gw[i] = f32(w[i].shape)
+        if i == 0:
+            _wgrad_input(planes, g[0], x_in, cin, cin8, n, gw[0], cin)
+        elif i == 4:       # W5 = [hidden 256 | xyz 3 | latent L]  (sdf_net.py:59)
+            raw.wgrad(L.MODE_DENSE, planes, g[4], HID, hs[3], (1, 1, 1, 1, HID), n, gw[4], sm=HID + cin, st=0, sc=1, m_valid=HID)
+            _wgrad_input(planes, g[4], x_in, cin, cin8, n, gw[4][:, HID:], HID + cin)
+        else:
+            raw.wgrad(L.MODE_DENSE, planes, g[i], HID, hs[i - 1], (1, 1, 1, 1, HID), n, gw[i], sm=HID, st=0, sc=1, m_valid=HID)
+    gpoints = glatent = None
+    if need_points or need_latent:
+        img = PACK_CACHE.get(w[0], 'sdf_t0', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8))
+        gx_a = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
+        raw.igemm(L.MODE_DENSE, planes, g[0], (1, 1, 1, 1, HID), n, HID, img, cin8, gx_a, cin8, n_pad=cin8)
+        img = PACK_CACHE.get(w[4], 'sdf_t4in', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8, col0=HID))
+        gx_b = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
+        raw.igemm(L.MODE_DENSE, planes, g[4], (1, 1, 1, 1, HID), n, HID, img, cin8, gx_b, cin8, n_pad=cin8)
+        gpoints = f32((n, 3)) if need_points else None
+        if need_latent:
+            glatent = torch.zeros((lat_rows, lat), dtype=torch.float32, device=dev) if indexed else f32((n, lat))
+        raw.sdf_unpack_grad(gx_a, gx_b, cin8, lat, index if indexed else None, gpoints, glatent)
+    grads = [gpoints, glatent, None, None]
+    for i in range(8):
+        grads.append(gw[i])
+        grads.append(gb[i])
+    return tuple(grads)
 
 
 def _wgrad_input(planes, g, x_in, cin, cin8, n, grad_view, ld):

@@ -392,6 +392,55 @@ def test_sdfnet_fused_kernel_matches_layerwise_path(monkeypatch):
         config.set_precision(old)
 
 
+def test_sdfnet_fused_persistent_loop_and_backward_chain(monkeypatch):
+    """bf16 mode, more tile pairs than SMs (every CTA of the persistent kernels loops: barrier phases, accumulator re-initialisation
+    and the weight ring wrap across pairs) with a ragged tail: fused forward against the CPU oracle; the fused input-gradient
+    chain (sg_sdfnet_bwd) against the layer-by-layer backward for EVERY parameter, the latent table and the points."""
+    from model.sdf_net import SDFNet
+    from shapegan_b200 import config
+    old = config.precision()
+    config.set_precision('bf16')
+    try:
+        net = SDFNet()
+        seeded_load(net, 4242)
+        n = 256 * 311 + 77
+        g = torch.Generator().manual_seed(19)
+        pts = (torch.rand((n, 3), generator=g) * 2 - 1).cuda()
+        table = (torch.randn((7, 128), generator=g) * 0.3).cuda()
+        idx = ((torch.arange(n) * 7) // n).to(torch.int32).cuda()
+        target = torch.clamp(pts.norm(dim=1) - 0.5, -0.1, 0.1)
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        ref = R.sdfnet_forward(sd, pts.cpu(), table.cpu()[idx.cpu().long()])
+        results = []
+        for mode in ('fused', 'fused_fwd_only', 'layerwise'):
+            if mode == 'fused_fwd_only':
+                monkeypatch.setenv('SG_B200_NO_FUSED_SDF_BWD', '1')
+            if mode == 'layerwise':
+                monkeypatch.setenv('SG_B200_NO_FUSED_SDF', '1')
+            net.zero_grad()
+            t = table.clone().requires_grad_(True)
+            x = pts.clone().requires_grad_(True)
+            out = net(x, t, idx)
+            torch.mean(torch.abs(out - target)).backward()
+            results.append((out.detach(), [t.grad.clone(), x.grad.clone()] + [q.grad.clone() for q in net.parameters()]))
+            monkeypatch.delenv('SG_B200_NO_FUSED_SDF_BWD', raising=False)
+            monkeypatch.delenv('SG_B200_NO_FUSED_SDF', raising=False)
+        names = ['latent_table', 'points'] + [k for k, _ in net.named_parameters()]
+        assert rel_l2(results[0][0], ref) < 3e-2 and rel_l2(results[2][0], ref) < 3e-2
+        assert rel_l2(results[0][0], results[2][0]) < 2e-2
+        lines, bad = [], []
+        for name, a, b, c in zip(names, results[0][1], results[1][1], results[2][1]):
+            e_chain, e_all = rel_l2(a, b), rel_l2(a, c)
+            lines.append('  %-22s fused-bwd vs layer-bwd (same fused fwd) %.2e   vs all-layerwise %.2e' % (name, e_chain, e_all))
+            if not (e_chain < 2e-2 and e_all < 6e-2):
+                bad.append(name)
+        print('\n' + '\n'.join(lines))
+        assert not bad, bad
+        check_dev()
+    finally:
+        config.set_precision(old)
+
+
 def test_wgan_step_flat_optimizer(prec):
     """The benchmarked step object (shapegan_b200.train.WGANStep: flat arenas, in-place weight-gradient accumulation, fused
     RMSprop+clip kernel, dead critic-wgrad elimination) against the reference's train_wgan.py:62-84 golden."""
