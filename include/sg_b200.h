@@ -193,13 +193,15 @@ typedef struct {
   const float* aux;
   float* out;
   void* stash;
+  void* mask_stash; /* optional uint32 [7][n][8]: ReLU mask of the 7 hidden activations, 1 bit per element (bit k of word j =
+                       column 32j+2k, bit 16+k = column 32j+2k+1); what sg_sdfnet_bwd reads instead of the activations */
 } sg_sdfnet_fwd_args;
 int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream);
 int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32_t* aux_floats);
 
 /* Fused input-gradient chain of the same MLP (what autograd runs for SDFNet.forward, model/sdf_net.py:56-61, between the
  * tanh head and layers1.0): g7 = gout*(1-out^2)*w8*[h7>0], then g_{l-1} = (g_l . W_l[:, :256]) * [h_{l-1}>0] for l = 7..2,
- * one persistent CTA per tile pair.  hstash = the forward's stash; wt_img = 24 chunks of 32 KB = sg_pack_b images of the
+ * one persistent CTA per tile pair.  mask_stash = the forward's 1-bit ReLU masks; wt_img = 24 chunks of 32 KB = sg_pack_b images of the
  * TRANSPOSED weights B[n = in-feature][k = out-feature] of layers2.4, layers2.2, layers2.0[:, :256], layers1.6, layers1.4,
  * layers1.2 (in that order); w8 = layers2.6.weight [256].  gstash receives g_1..g_7 as bf16 [7][n][256] (index l-1): the
  * operands of the weight-gradient GEMMs, bias sums and the two input-gradient GEMMs (sg_wgrad / sg_act_bwd / sg_igemm).
@@ -208,7 +210,7 @@ int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32_t* aux_flo
 typedef struct {
   const float* gout; /* [n] gradient w.r.t. the tanh output */
   const float* out;  /* [n] the forward's output */
-  const void* hstash;
+  const void* mask_stash;
   const void* wt_img;
   const float* w8;
   int64_t n;

@@ -46,11 +46,11 @@ class SgPackBArgs(ctypes.Structure):
 
 class SgSdfnetFwdArgs(ctypes.Structure):
     _fields_ = [('points', c_void_p), ('latent', c_void_p), ('index', c_void_p), ('n', c_int64), ('w_img', c_void_p),
-                ('aux', c_void_p), ('out', c_void_p), ('stash', c_void_p)]
+                ('aux', c_void_p), ('out', c_void_p), ('stash', c_void_p), ('mask_stash', c_void_p)]
 
 
 class SgSdfnetBwdArgs(ctypes.Structure):
-    _fields_ = [('gout', c_void_p), ('out', c_void_p), ('hstash', c_void_p), ('wt_img', c_void_p), ('w8', c_void_p),
+    _fields_ = [('gout', c_void_p), ('out', c_void_p), ('mask_stash', c_void_p), ('wt_img', c_void_p), ('w8', c_void_p),
                 ('n', c_int64), ('gstash', c_void_p)]
 
 

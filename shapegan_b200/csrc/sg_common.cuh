@@ -202,6 +202,11 @@ __device__ __forceinline__ void stg_256(void* p, uint4 a, uint4 b) {
                : "memory");
 }
 
+// pull `bytes` (multiple of 16) of global memory into L2 ahead of the loads that will need them
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // byte offset of 16-byte piece `piece` of row `row` inside a 128B-swizzled [rows][128 B] tile (tile base 1024 B aligned)
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t piece) { return row * 128u + ((piece ^ (row & 7u)) << 4); }
 

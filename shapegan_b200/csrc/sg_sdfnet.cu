@@ -12,14 +12,16 @@
 //                                 L6(4) L7(4); the hidden chunks feed BOTH tiles
 //   CONST : biases, xyz columns, the 256 -> 1 head (14 KB, uploaded per launch): uniform reads that do not touch the
 //           2 KB of L1 this kernel's shared-memory carve-out leaves
-//   warps : 0 weight loader (1-D TMA bulk copies) | 1 MMA issuer (tcgen05.mma M128 N256 K16) | 4-7 latent gather |
-//           8-11 epilogue of tile A | 12-15 epilogue of tile B
+//   warps : 0 weight loader (1-D TMA bulk copies) | 1 MMA issuer (tcgen05.mma M128 N256 K16) | 2-5 latent gather |
+//           6-13 epilogue of tile A | 14-21 epilogue of tile B; an epilogue warp owns TMEM lane quadrant warp%4 (32 rows) and one
+//           column half (128 columns): four epilogue warps per scheduler hide each other's TMEM / constant-bank latencies
 //   Layer 8 (256 -> 1) + tanh is a per-row dot product folded into the epilogue of layer 7.
 //
 // BACKWARD sg_sdfnet_bwd_kernel: the input-gradient chain g7 -> g6 -> ... -> g1 of a tile pair inside one CTA
 //   (g_l = gradient w.r.t. the pre-activation of layer l).  Head: g7 = gout (1 - out^2) w8 [h7 > 0]; layers 7..2:
 //   g_{l-1} = (g_l W_l[:, :256]) [h_{l-1} > 0] with g_l as the SMEM A operand, W_l^T streamed (24 chunks / pair, 3 stages),
-//   the ReLU mask read from the forward stash as 1 bit per element while the MMAs run.  Every g_l is written to `gstash`
+//   the ReLU mask read as 1 bit per element from the forward's mask stash (32 B per row and layer), one step ahead of its use.
+//   Every g_l is written to `gstash`
 //   (bf16 [7][n][256]) for the weight-gradient GEMMs, the bias sums and the two input-gradient GEMMs that follow.
 #include <algorithm>
 #include <cstring>
@@ -29,7 +31,8 @@
 
 namespace sg {
 
-constexpr int kSdfThreads = 512;
+constexpr int kSdfThreads = 704;
+constexpr uint32_t kOffDot = 1024;           // float[2][128] inside the header block: column-half partial sums of the 256 -> 1 head
 constexpr int kSdfImgChunks = 28;       // chunks in the weight image
 constexpr int kSdfStreamChunks = 30;    // chunks streamed per tile pair (the 2 latent chunks of layers2.0 twice)
 constexpr uint32_t kChunkBytes = 32768;
@@ -49,14 +52,14 @@ struct SdfHdr {
 
 struct SdfP {
   const float* points; const float* latent; const int* index; long long n;
-  const char* w_img; float* out; bf16* stash;
+  const char* w_img; float* out; bf16* stash; uint32_t* mstash;
   long long pairs;
   int* err;
 };
 
 // aux layout (floats)
-constexpr int kAuxXb1 = 0;          // float4[256] {w_x, w_y, w_z, bias} of layers1.0
-constexpr int kAuxXb5 = 1024;       // float4[256] of layers2.0
+constexpr int kAuxXb1 = 0;          // layers1.0, per column PAIR (c, c+1): {wx_c, wx_c1, wy_c, wy_c1, wz_c, wz_c1, b_c, b_c1} (fma.rn.f32x2 operands)
+constexpr int kAuxXb5 = 1024;       // same for layers2.0
 constexpr int kAuxBias = 2048;      // [5][256]: layers1.2, 1.4, 1.6, layers2.2, 2.4
 constexpr int kAuxW8 = 2048 + 5 * 256;
 constexpr int kAuxB8 = kAuxW8 + 256;
@@ -65,18 +68,32 @@ constexpr int kAuxFloats = kAuxB8 + 1;
 __constant__ float c_sdf_aux[kAuxFloats];     // forward: see above; uploaded (device -> device) by sg_sdfnet_fwd on its stream
 __constant__ float c_sdf_w8[256];             // backward: layers2.6 weight row
 
-// fp32 value the accumulator of layer `l` starts from, columns [c0, c0+32) of the row at (px, py, pz)
-__device__ __forceinline__ void sdf_acc_init(int l, int c0, float px, float py, float pz, uint32_t (&v)[32]) {
+__device__ __forceinline__ unsigned long long f32x2_bcast(float a) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(a));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// fp32 value the accumulator of layer `l` starts from, columns [col, col+32) of the row at (px, py, pz)
+__device__ __forceinline__ void sdf_acc_init(int l, int col, float px, float py, float pz, uint32_t (&v)[32]) {
   if (l == 1 || l == 5) {
-    const float4* xb = reinterpret_cast<const float4*>(c_sdf_aux + (l == 1 ? kAuxXb1 : kAuxXb5)) + c0;
+    const unsigned long long* xb = reinterpret_cast<const unsigned long long*>(c_sdf_aux + (l == 1 ? kAuxXb1 : kAuxXb5)) + (col >> 1) * 4;
+    const unsigned long long x2 = f32x2_bcast(px), y2 = f32x2_bcast(py), z2 = f32x2_bcast(pz);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float4 w = xb[j];
-      v[j] = __float_as_uint(fmaf(w.x, px, fmaf(w.y, py, fmaf(w.z, pz, w.w))));
+    for (int j = 0; j < 16; ++j) {
+      unsigned long long d = fma_f32x2(xb[4 * j + 2], z2, xb[4 * j + 3]);
+      d = fma_f32x2(xb[4 * j + 1], y2, d);
+      d = fma_f32x2(xb[4 * j], x2, d);
+      v[2 * j] = (uint32_t)d; v[2 * j + 1] = (uint32_t)(d >> 32);
     }
   } else {
     const int bslot = (l < 5) ? l - 2 : l - 3;            // layers 2,3,4 -> 0,1,2 ; layers 6,7 -> 3,4
-    const float* b = c_sdf_aux + kAuxBias + bslot * 256 + c0;
+    const float* b = c_sdf_aux + kAuxBias + bslot * 256 + col;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(b[j]);
   }
@@ -85,11 +102,12 @@ __device__ __forceinline__ void sdf_acc_init(int l, int c0, float px, float py, 
 __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __grid_constant__ SdfP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SdfHdr* hdr = reinterpret_cast<SdfHdr*>(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // broadcast: the compiler can keep everything derived from it uniform
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&hdr->w_full[i], 1); mbar_init(&hdr->w_empty[i], 1);
-      mbar_init(&hdr->acc_full[i], 1); mbar_init(&hdr->h_ready[i], 128);
+      mbar_init(&hdr->acc_full[i], 1); mbar_init(&hdr->h_ready[i], 256);
     }
     mbar_init(&hdr->lat_full, 128); mbar_init(&hdr->lat_empty, 1);
     fence_mbar_init();
@@ -190,24 +208,25 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 2 && warp < 6) {
     // ================================================================ latent gather: fp32 table rows -> bf16 swizzled A tile
-    const int gw = warp - 4;
+    const int gw = warp - 2;
     uint32_t use = 0;
     for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
       for (int u = 0; u < 4; ++u, ++use) {          // (A,L1) (B,L1) (A,L5) (B,L5)
         const long long tile = pr * 2 + (u & 1);
         if (use > 0) mbar_wait(&hdr->lat_empty, (use - 1) & 1u, p.err);
         const int chunk = lane >> 4, piece = (lane & 15) >> 1, half = lane & 1;
-#pragma unroll 8
+        // table row of each of this warp's 32 points: one coalesced index load, broadcast by shuffle (no dependent load chain)
+        const long long gr_l = tile * kTileRows + gw * 32 + lane;
+        long long my_row = -1;
+        if (gr_l < p.n) my_row = p.index ? (long long)__ldg(p.index + gr_l) : gr_l;
+#pragma unroll 16
         for (int i = 0; i < 32; ++i) {
           const int r = gw * 32 + i;
-          const long long gr = tile * kTileRows + r;
+          const long long lrow = __shfl_sync(0xffffffffu, my_row, i);
           float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gr < p.n) {
-            const long long lrow = p.index ? (long long)__ldg(p.index + gr) : gr;
-            f = __ldg(reinterpret_cast<const float4*>(p.latent + lrow * 128) + lane);
-          }
+          if (lrow >= 0) f = __ldg(reinterpret_cast<const float4*>(p.latent + lrow * 128) + lane);
           uint2 v;
           v.x = pack_bf16x2(f.x, f.y); v.y = pack_bf16x2(f.z, f.w);
           *reinterpret_cast<uint2*>(smem + kOffLat + chunk * kTileBytes + sw128((uint32_t)r, (uint32_t)piece) + half * 8) = v;
@@ -216,22 +235,26 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         mbar_arrive(&hdr->lat_full);
       }
     }
-  } else if (warp >= 8) {
-    // ================================================================ epilogue of tile t (t = 0: warps 8-11, t = 1: warps 12-15)
-    const int t = (warp - 8) >> 2;
+  } else if (warp >= 6) {
+    // ================================================================ epilogue: tile t, lane quadrant q (32 rows), column half
+    const int e = warp - 6;
+    const int t = e >> 3, half = (e >> 2) & 1;
     const int q = warp & 3;
     const int r = q * 32 + lane;
+    const int cbase = half * 128;
     uint8_t* hbuf = smem + (t ? kOffHB : kOffHA);
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    float* dotbuf = reinterpret_cast<float*>(smem + kOffDot) + t * 128;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cbase);
     uint32_t af_n = 0;
     float px = 0.f, py = 0.f, pz = 0.f;
     {
       const long long gr = ((long long)blockIdx.x * 2 + t) * kTileRows + r;
-      if (blockIdx.x < p.pairs && gr < p.n) { px = __ldg(p.points + gr * 3); py = __ldg(p.points + gr * 3 + 1); pz = __ldg(p.points + gr * 3 + 2); }
+      if (gr < p.n) { px = __ldg(p.points + gr * 3); py = __ldg(p.points + gr * 3 + 1); pz = __ldg(p.points + gr * 3 + 2); }
       // accumulator of layer 1 of the first pair
-      for (int c0 = 0; c0 < 256; c0 += 32) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t iv[32];
-        sdf_acc_init(1, c0, px, py, pz, iv);
+        sdf_acc_init(1, cbase + c0, px, py, pz, iv);
         tmem_st32(t_addr + c0, iv);
       }
       tmem_st_wait();
@@ -253,9 +276,11 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         const bool init_next = (l < 7) || (npr < p.pairs);
         const float ix = (l < 7) ? px : nx, iy = (l < 7) ? py : ny, iz = (l < 7) ? pz : nz;
         float dot = 0.f;
-        bf16* srow = (p.stash != nullptr && valid) ? p.stash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 256 : nullptr;
+        bf16* srow = (p.stash != nullptr && valid) ? p.stash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 256 + cbase : nullptr;
+        uint32_t* mrow = (p.mstash != nullptr && valid) ? p.mstash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 8 + half * 4 : nullptr;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          const int col = cbase + c0;
           uint32_t acc[32];
           tmem_ld32(t_addr + c0, acc);
           tmem_ld_wait();
@@ -268,12 +293,12 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
             pk[u].w = pack_relu_bf16x2(__uint_as_float(acc[u * 8 + 6]), __uint_as_float(acc[u * 8 + 7]));
           }
           if (l < 7) {
-            const uint32_t chunk = (uint32_t)c0 >> 6, pbase = ((uint32_t)c0 & 63u) >> 3;
+            const uint32_t chunk = (uint32_t)col >> 6, pbase = ((uint32_t)col & 63u) >> 3;
 #pragma unroll
             for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
           } else {
             // layers2.6 (256 -> 1) on the bf16-rounded activations (what the backward sees in the stash)
-            const float* w8 = c_sdf_aux + kAuxW8 + c0;
+            const float* w8 = c_sdf_aux + kAuxW8 + col;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               dot = fmaf(bf16lo_to_f(pk[u].x), w8[u * 8], dot); dot = fmaf(bf16hi_to_f(pk[u].x), w8[u * 8 + 1], dot);
@@ -283,13 +308,27 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
             }
           }
           if (srow) { stg_256(srow + c0, pk[0], pk[1]); stg_256(srow + c0 + 16, pk[2], pk[3]); }
+          if (mrow) {
+            // ReLU mask of these 32 columns, 1 bit each (bit k = column 2k, bit 16+k = column 2k+1): the backward chain reads
+            // 32 B per row and layer instead of the 512 B activation row.  h >= 0, so (h + 0x7fff) carries into bit 15 iff h != 0.
+            const uint32_t w[16] = {pk[0].x, pk[0].y, pk[0].z, pk[0].w, pk[1].x, pk[1].y, pk[1].z, pk[1].w,
+                                    pk[2].x, pk[2].y, pk[2].z, pk[2].w, pk[3].x, pk[3].y, pk[3].z, pk[3].w};
+            uint32_t bits = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) bits |= ((w[k] + 0x7fff7fffu) >> (15 - k)) & (0x00010001u << k);
+            mrow[c0 >> 5] = bits;
+          }
           if (init_next) {
             uint32_t iv[32];
-            sdf_acc_init(nl, c0, ix, iy, iz, iv);
+            sdf_acc_init(nl, col, ix, iy, iz, iv);
             tmem_st32(t_addr + c0, iv);
           }
         }
-        if (l == 7 && valid) p.out[gr] = tanhf(dot + c_sdf_aux[kAuxB8]);
+        if (l == 7) {       // the two column halves of a row meet through shared memory (named barrier of the tile's 8 warps)
+          if (half == 1) dotbuf[r] = dot;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+          if (half == 0 && valid) p.out[gr] = tanhf(dot + dotbuf[r] + c_sdf_aux[kAuxB8]);
+        }
         tmem_st_wait();
         if (l < 7) fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
         tc_fence_before();
@@ -304,14 +343,14 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
-constexpr int kSdfBwdThreads = 384;     // 0 weight loader | 1 MMA issuer | 4-7 epilogue of tile A | 8-11 epilogue of tile B
+constexpr int kSdfBwdThreads = 576;     // 0 weight loader | 1 MMA issuer | 2-9 epilogue of tile A | 10-17 epilogue of tile B (quadrant x column half)
 constexpr int kSdfBwdChunks = 24;       // W7^T, W6^T, W5[:, :256]^T, W4^T, W3^T, W2^T, 4 chunks each
 constexpr int kSdfBwdStages = 3;
 constexpr uint32_t kOffBW = kOffHB + 65536;
 constexpr uint32_t kSdfBwdSmem = kOffBW + kSdfBwdStages * kChunkBytes;      // 231424 B
 
 struct SdfBwdP {
-  const float* gout; const float* out; const bf16* hstash; const char* wt_img; bf16* gstash;
+  const float* gout; const float* out; const uint32_t* mstash; const char* wt_img; bf16* gstash;
   long long n, pairs;
   int* err;
 };
@@ -319,10 +358,11 @@ struct SdfBwdP {
 __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const __grid_constant__ SdfBwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SdfHdr* hdr = reinterpret_cast<SdfHdr*>(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // broadcast: the compiler can keep everything derived from it uniform
   if (tid == 0) {
     for (int i = 0; i < kSdfBwdStages; ++i) { mbar_init(&hdr->w_full[i], 1); mbar_init(&hdr->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&hdr->acc_full[i], 1); mbar_init(&hdr->h_ready[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hdr->acc_full[i], 1); mbar_init(&hdr->h_ready[i], 256); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&hdr->tmem_base, 512);
@@ -376,111 +416,89 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
         }
       }
     }
-  } else if (warp >= 4) {
-    // ================================================================ epilogue of tile t
-    const int t = (warp - 4) >> 2;
+  } else if (warp >= 2) {
+    // ================================================================ epilogue: tile t, lane quadrant q (32 rows), column half
+    const int e = warp - 2;
+    const int t = e >> 3, half = (e >> 2) & 1;
     const int q = warp & 3;
     const int r = q * 32 + lane;
+    const int cbase = half * 128;
     uint8_t* hbuf = smem + (t ? kOffHB : kOffHA);
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cbase);
+    // step s of a pair reads mstash[6 - s] (s = 0: head, s = 8 - l: the mask of layer l's epilogue): 16 bytes per thread, fetched
+    // one step ahead of its use
+    auto load_mask = [&](long long pair, int sidx) -> uint4 {
+      const long long g = (pair * 2 + t) * kTileRows + r;
+      if (pair >= p.pairs || g >= p.n) return make_uint4(0u, 0u, 0u, 0u);
+      return __ldg(reinterpret_cast<const uint4*>(p.mstash + ((size_t)(6 - sidx) * (size_t)p.n + (size_t)g) * 8 + half * 4));
+    };
     uint32_t af_n = 0;
+    uint4 mcur = load_mask(blockIdx.x, 0);
     for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
       const long long gr = (pr * 2 + t) * kTileRows + r;
       const bool valid = gr < p.n;
+      const long long npr = pr + gridDim.x;
       // ---------- head: g7 = gout * tanh'(out) * w8 where h7 > 0 (model/sdf_net.py:50-51)
       {
+        const uint4 mnext = load_mask(pr, 1);
         float s = 0.f;
         if (valid) { const float o = __ldg(p.out + gr); s = __ldg(p.gout + gr) * (1.f - o * o); }
-        const bf16* hrow = p.hstash + ((size_t)6 * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
-        bf16* grow = p.gstash + ((size_t)6 * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
-#pragma unroll 2
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          u32x8 hv[2];
+        bf16* grow = p.gstash + ((size_t)6 * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256 + cbase;
+        const uint32_t mb[4] = {mcur.x, mcur.y, mcur.z, mcur.w};
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (valid) hv[u] = ldg_nc_256(hrow + c0 + u * 16);
-            else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) hv[u].v[k] = 0u;
-            }
-          }
-          const float* w8 = c_sdf_w8 + c0;
+        for (int c = 0; c < 4; ++c) {
+          const int col = cbase + c * 32;
+          const float* w8 = c_sdf_w8 + col;
+          const uint32_t bits = mb[c];
           uint32_t o[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const uint32_t hw = hv[k >> 3].v[k & 7];
-            const float lo = (hw & 0x7fffu) ? s * w8[2 * k] : 0.f;
-            const float hi = (hw & 0x7fff0000u) ? s * w8[2 * k + 1] : 0.f;
+            const float lo = ((bits >> k) & 1u) ? s * w8[2 * k] : 0.f;
+            const float hi = ((bits >> (16 + k)) & 1u) ? s * w8[2 * k + 1] : 0.f;
             o[k] = pack_bf16x2(lo, hi);
           }
           uint4 pk[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) pk[u] = make_uint4(o[u * 4], o[u * 4 + 1], o[u * 4 + 2], o[u * 4 + 3]);
-          const uint32_t chunk = (uint32_t)c0 >> 6, pbase = ((uint32_t)c0 & 63u) >> 3;
+          const uint32_t chunk = (uint32_t)col >> 6, pbase = ((uint32_t)col & 63u) >> 3;
 #pragma unroll
           for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
-          if (valid) { stg_256(grow + c0, pk[0], pk[1]); stg_256(grow + c0 + 16, pk[2], pk[3]); }
+          if (valid) { stg_256(grow + c * 32, pk[0], pk[1]); stg_256(grow + c * 32 + 16, pk[2], pk[3]); }
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&hdr->h_ready[t]);
+        mcur = mnext;
       }
       // ---------- layers 7..2: g_{l-1} = (g_l W_l) [h_{l-1} > 0]
       for (int l = 7; l >= 2; --l) {
-        // ReLU mask of h_{l-1}, one bit per column of this thread's row, fetched while the MMAs of this layer run
-        uint32_t mb[8];
-        {
-          const bf16* hrow = p.hstash + ((size_t)(l - 2) * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {       // two rounds of 8 x 32-byte loads: 64 registers in flight, not 128
-            u32x8 hv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (valid) hv[i] = ldg_nc_256(hrow + half * 128 + i * 16);
-              else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) hv[i].v[k] = 0u;
-              }
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              uint32_t bits = 0;
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const uint32_t hw = hv[cc * 2 + (k >> 3)].v[k & 7];
-                bits |= ((hw & 0x7fffu) ? 1u : 0u) << (2 * k);
-                bits |= ((hw & 0x7fff0000u) ? 1u : 0u) << (2 * k + 1);
-              }
-              asm volatile("" : "+r"(bits));           // keeps the extraction of this round ahead of the next round's loads
-              mb[half * 4 + cc] = bits;
-            }
-          }
-        }
+        const int sn = (8 - l) + 1;                                   // next step: of this pair, or the head of this CTA's next pair
+        const uint4 mnext = (sn <= 6) ? load_mask(pr, sn) : load_mask(npr, 0);
         mbar_wait(&hdr->acc_full[t], af_n & 1u, p.err); ++af_n;
         tc_fence_after();
-        bf16* grow = p.gstash + ((size_t)(l - 2) * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int c0 = c * 32;
+        bf16* grow = p.gstash + ((size_t)(l - 2) * (size_t)p.n + (size_t)(valid ? gr : 0)) * 256 + cbase;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = c * 32, col = cbase + c0;
           uint32_t acc[32];
           tmem_ld32(t_addr + c0, acc);
           tmem_ld_wait();
-          const uint32_t bits = mb[c];
+          const uint32_t bits = c == 0 ? mcur.x : (c == 1 ? mcur.y : (c == 2 ? mcur.z : mcur.w));
           uint4 pk[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint32_t o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int e = u * 8 + 2 * k;
-              const float lo = ((bits >> e) & 1u) ? __uint_as_float(acc[e]) : 0.f;
-              const float hi = ((bits >> (e + 1)) & 1u) ? __uint_as_float(acc[e + 1]) : 0.f;
+              const int wd = u * 4 + k;                              // bf16x2 word: columns 2*wd (bit wd) and 2*wd+1 (bit 16+wd)
+              const float lo = ((bits >> wd) & 1u) ? __uint_as_float(acc[2 * wd]) : 0.f;
+              const float hi = ((bits >> (16 + wd)) & 1u) ? __uint_as_float(acc[2 * wd + 1]) : 0.f;
               o[k] = pack_bf16x2(lo, hi);
             }
             pk[u] = make_uint4(o[0], o[1], o[2], o[3]);
           }
           if (l > 2) {
-            const uint32_t chunk = (uint32_t)c0 >> 6, pbase = ((uint32_t)c0 & 63u) >> 3;
+            const uint32_t chunk = (uint32_t)col >> 6, pbase = ((uint32_t)col & 63u) >> 3;
 #pragma unroll
             for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
           }
@@ -493,6 +511,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
         } else {
           tc_fence_before();      // orders the accumulator reads before the head of the next pair arrives on h_ready
         }
+        mcur = mnext;
       }
     }
   }
@@ -511,7 +530,7 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   SdfP p;
   memset(&p, 0, sizeof(p));
   p.points = a->points; p.latent = a->latent; p.index = a->index; p.n = a->n;
-  p.w_img = (const char*)a->w_img; p.out = a->out; p.stash = (bf16*)a->stash;
+  p.w_img = (const char*)a->w_img; p.out = a->out; p.stash = (bf16*)a->stash; p.mstash = (uint32_t*)a->mask_stash;
   const long long tiles = (a->n + kTileRows - 1) / kTileRows;
   p.pairs = (tiles + 1) / 2;
   p.err = sg_error_word();
@@ -538,11 +557,11 @@ extern "C" int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32
 }
 
 extern "C" int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream) {
-  if (!a || !a->gout || !a->out || !a->hstash || !a->wt_img || !a->w8 || !a->gstash) return sg_fail(-1, "sg_sdfnet_bwd: null");
+  if (!a || !a->gout || !a->out || !a->mask_stash || !a->wt_img || !a->w8 || !a->gstash) return sg_fail(-1, "sg_sdfnet_bwd: null");
   if (a->n <= 0) return 0;
   SdfBwdP p;
   memset(&p, 0, sizeof(p));
-  p.gout = a->gout; p.out = a->out; p.hstash = (const bf16*)a->hstash; p.wt_img = (const char*)a->wt_img; p.gstash = (bf16*)a->gstash;
+  p.gout = a->gout; p.out = a->out; p.mstash = (const uint32_t*)a->mask_stash; p.wt_img = (const char*)a->wt_img; p.gstash = (bf16*)a->gstash;
   p.n = a->n;
   const long long tiles = (a->n + kTileRows - 1) / kTileRows;
   p.pairs = (tiles + 1) / 2;

@@ -339,19 +339,19 @@ def sum_f32(x):
     return out
 
 
-def sdfnet_fwd(points, latent, index, w_img, aux, stash=None):
+def sdfnet_fwd(points, latent, index, w_img, aux, stash=None, mask_stash=None):
     n = points.shape[0]
     out = torch.empty(n, dtype=torch.float32, device=points.device)
-    a = L.SgSdfnetFwdArgs(_p(points), _p(latent), _p(index), n, _p(w_img), _p(aux), _p(out), _p(stash))
+    a = L.SgSdfnetFwdArgs(_p(points), _p(latent), _p(index), n, _p(w_img), _p(aux), _p(out), _p(stash), _p(mask_stash))
     L.check(L.lib().sg_sdfnet_fwd(ctypes.byref(a), stream()), 'sg_sdfnet_fwd')
     return out
 
 
-def sdfnet_bwd(gout, out, hstash, wt_img, w8):
+def sdfnet_bwd(gout, out, mask_stash, wt_img, w8):
     """Fused input-gradient chain (sg_sdfnet.cu): returns gstash bf16 [7, n, 256] = gradients w.r.t. the pre-activations
     of layers 1..7."""
     n = out.shape[0]
     gstash = torch.empty((7, n, 256), dtype=torch.bfloat16, device=out.device)
-    a = L.SgSdfnetBwdArgs(_p(gout), _p(out), _p(hstash), _p(wt_img), _p(w8), n, _p(gstash))
+    a = L.SgSdfnetBwdArgs(_p(gout), _p(out), _p(mask_stash), _p(wt_img), _p(w8), n, _p(gstash))
     L.check(L.lib().sg_sdfnet_bwd(ctypes.byref(a), stream()), 'sg_sdfnet_bwd')
     return gstash

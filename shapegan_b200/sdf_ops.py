@@ -61,8 +61,9 @@ def _fused_pack(w, b):
     for i in (5, 6):
         put(w[i].detach(), 256)
     assert off == 28 * chunk
-    xb1 = torch.cat((w1[:, 0:3], b[0].detach().unsqueeze(1)), 1)
-    xb5 = torch.cat((w5[:, 256:259], b[4].detach().unsqueeze(1)), 1)
+    # per column pair (c, c+1): {wx_c, wx_c1, wy_c, wy_c1, wz_c, wz_c1, b_c, b_c1} -- the fma.rn.f32x2 operand order of sg_sdfnet.cu
+    xb1 = torch.cat((w1[:, 0:3], b[0].detach().unsqueeze(1)), 1).reshape(128, 2, 4).permute(0, 2, 1)
+    xb5 = torch.cat((w5[:, 256:259], b[4].detach().unsqueeze(1)), 1).reshape(128, 2, 4).permute(0, 2, 1)
     aux = torch.cat([xb1.reshape(-1), xb5.reshape(-1)] + [b[i].detach() for i in (1, 2, 3, 5, 6)] +
                     [w[7].detach().reshape(-1), b[7].detach().reshape(-1)]).contiguous().float()
     if not torch.cuda.is_current_stream_capturing():
@@ -91,12 +92,14 @@ class SDFNetFunction(Function):
             # fused persistent kernel: all 8 layers per tile pair in one CTA (sg_sdfnet.cu)
             img, aux = _fused_pack(w, b)
             stash = torch.empty((7, n, HID), dtype=torch.bfloat16, device=dev) if need_graph else None
-            out = raw.sdfnet_fwd(points, latent, index, img, aux, stash)
+            mstash = torch.empty((7, n, 8), dtype=torch.int32, device=dev) if need_graph else None      # 1-bit ReLU masks
+            out = raw.sdfnet_fwd(points, latent, index, img, aux, stash, mstash)
             if need_graph:
                 x_in = raw.sdf_pack_input(points, latent, index, lat, planes, cin8)
                 ctx.meta = (planes, n, lat, cin, cin8, index is not None, latent.shape[0])
                 ctx.w_objs = w
                 ctx.fused = True
+                ctx.mstash = mstash
                 ctx.save_for_backward(x_in, out, index if index is not None else torch.empty(0, device=dev), stash, *w)
             return out
         ctx.fused = False
@@ -153,7 +156,7 @@ class SDFNetFunction(Function):
             return torch.empty(shape, dtype=torch.float32, device=dev)
 
         if ctx.fused and fused_bwd_enabled():
-            return _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, hstash, hs, w, gout,
+            return _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, ctx.mstash, hs, w, gout,
                                    need_points, need_latent, need_w, need_b)
 
         # ---- head: Linear(256->1) + tanh
@@ -232,7 +235,7 @@ def _fused_pack_t(w):
     return img
 
 
-def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, hstash, hs, w, gout, need_points, need_latent, need_w,
+def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, mstash, hs, w, gout, need_points, need_latent, need_w,
                     need_b):
     """Backward of the fused forward: ONE persistent kernel runs the whole input-gradient chain (sg_sdfnet_bwd) and leaves
     g_1..g_7 in a bf16 stash; the weight gradients, bias sums and the two input-gradient GEMMs read that stash."""
@@ -243,12 +246,12 @@ def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, ind
 
     gw = [None] * 8
     gb = [None] * 8
-    assert hstash.shape == (7, n, HID) and hstash.is_contiguous()
+    assert mstash.shape == (7, n, 8) and mstash.is_contiguous()
     if need_w[7] or need_b[7]:
         _, sums = raw.rowdot_bwd(gout, out, L.ACT_TANH, hs[6], HID, w[7], False, True, planes, n)
         gw[7] = raw.emit_sums(sums, f32(w[7].shape), HID)
         gb[7] = raw.emit_sums(sums[HID:], f32((1,)), 1)
-    gst = raw.sdfnet_bwd(gout, out, hstash, _fused_pack_t(w), w[7].detach().reshape(-1))
+    gst = raw.sdfnet_bwd(gout, out, mstash, _fused_pack_t(w), w[7].detach().reshape(-1))
     g = [gst[i].unsqueeze(0) for i in range(7)]                                     # g[i]: gradient w.r.t. the pre-activation of layer i+1
     for i in range(7):
         if need_b[i]:
