@@ -24,10 +24,12 @@
 //   Every g_l is written to `gstash`
 //   (bf16 [7][n][256]) for the weight-gradient GEMMs, the bias sums and the two input-gradient GEMMs that follow.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "sg_common.cuh"
 #include "sg_internal.h"
+#include "sg_tma.h"
 
 namespace sg {
 
@@ -55,6 +57,8 @@ struct SdfP {
   const char* w_img; float* out; bf16* stash; uint32_t* mstash;
   long long pairs;
   int* err;
+  int tma_stash;            // stash rows of layers 1..6 leave through TMA tile stores out of the activation tiles in SMEM
+  CUtensorMap tm_stash;     // bf16 [7][n][256], box [1][128][64], 128B swizzle
 };
 
 // aux layout (floats)
@@ -173,6 +177,12 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         // h[t] holds the activations of layer l-1 and accumulator t is drained and re-initialised
         for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }
         tc_fence_after();
+        if (p.tma_stash && l >= 2 && lane == 0) {      // h_{l-1} of both tiles: SMEM tiles -> stash[l-2] (rows >= n are clipped)
+          for (int t = 0; t < 2; ++t)
+            for (int c = 0; c < 4; ++c)
+              tma_store_3d(&p.tm_stash, s_base + (t ? kOffHB : kOffHA) + c * kTileBytes, c * 64, (int)((pr * 2 + t) * kTileRows), l - 2);
+          tma_store_commit();
+        }
         if (l == 1) {
           wait_two_chunks();
           latent_mma(0, true);
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
               const uint32_t a = s_base + (t ? kOffHB : kOffHA) + c * kTileBytes;
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, 1u);
+              if (c == 3 && t == 0 && p.tma_stash) tma_store_wait_read();   // the epilogue overwrites the tiles after acc_full
               if (c == 3 && (l != 5 || t == 0)) umma_commit(&hdr->acc_full[t]);
             }
             umma_commit(&hdr->w_empty[g & 1u]);
@@ -208,6 +219,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         }
       }
     }
+    if (p.tma_stash && lane == 0) tma_store_wait_all();
   } else if (warp >= 2 && warp < 6) {
     // ================================================================ latent gather: fp32 table rows -> bf16 swizzled A tile
     const int gw = warp - 2;
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         const bool init_next = (l < 7) || (npr < p.pairs);
         const float ix = (l < 7) ? px : nx, iy = (l < 7) ? py : ny, iz = (l < 7) ? pz : nz;
         float dot = 0.f;
-        bf16* srow = (p.stash != nullptr && valid) ? p.stash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 256 + cbase : nullptr;
+        bf16* srow = (p.stash != nullptr && valid && (l == 7 || !p.tma_stash)) ? p.stash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 256 + cbase : nullptr;
         uint32_t* mrow = (p.mstash != nullptr && valid) ? p.mstash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 8 + half * 4 : nullptr;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -353,6 +365,8 @@ struct SdfBwdP {
   const float* gout; const float* out; const uint32_t* mstash; const char* wt_img; bf16* gstash;
   long long n, pairs;
   int* err;
+  int tma_stash;            // g_7..g_2 leave through TMA tile stores out of the operand tiles in SMEM
+  CUtensorMap tm_stash;     // bf16 [7][n][256], box [1][128][64], 128B swizzle
 };
 
 __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const __grid_constant__ SdfBwdP p) {
@@ -397,6 +411,12 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
       for (int l = 7; l >= 2; --l) {
         for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }   // g_l in SMEM, accumulator drained
         tc_fence_after();
+        if (p.tma_stash && lane == 0) {               // g_l of both tiles: SMEM operand tiles -> gstash[l-1] (rows >= n are clipped)
+          for (int t = 0; t < 2; ++t)
+            for (int c = 0; c < 4; ++c)
+              tma_store_3d(&p.tm_stash, s_base + (t ? kOffHB : kOffHA) + c * kTileBytes, c * 64, (int)((pr * 2 + t) * kTileRows), l - 1);
+          tma_store_commit();
+        }
         for (int c = 0; c < 4; ++c) {
           mbar_wait(&hdr->w_full[st], ph, p.err);
           tc_fence_after();
@@ -407,6 +427,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
               const uint32_t a = s_base + (t ? kOffHB : kOffHA) + c * kTileBytes;
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, (c | kk) ? 1u : 0u);
+              if (c == 3 && t == 0 && p.tma_stash) tma_store_wait_read();   // the epilogue overwrites the tiles after acc_full
               if (c == 3) umma_commit(&hdr->acc_full[t]);
             }
             umma_commit(&hdr->w_empty[st]);
@@ -416,6 +437,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
         }
       }
     }
+    if (p.tma_stash && lane == 0) tma_store_wait_all();
   } else if (warp >= 2) {
     // ================================================================ epilogue: tile t, lane quadrant q (32 rows), column half
     const int e = warp - 2;
@@ -463,7 +485,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
           const uint32_t chunk = (uint32_t)col >> 6, pbase = ((uint32_t)col & 63u) >> 3;
 #pragma unroll
           for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
-          if (valid) { stg_256(grow + c * 32, pk[0], pk[1]); stg_256(grow + c * 32 + 16, pk[2], pk[3]); }
+          if (valid && !p.tma_stash) { stg_256(grow + c * 32, pk[0], pk[1]); stg_256(grow + c * 32 + 16, pk[2], pk[3]); }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -502,7 +524,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
 #pragma unroll
             for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
           }
-          if (valid) { stg_256(grow + c0, pk[0], pk[1]); stg_256(grow + c0 + 16, pk[2], pk[3]); }
+          if (valid && (l == 2 || !p.tma_stash)) { stg_256(grow + c0, pk[0], pk[1]); stg_256(grow + c0 + 16, pk[2], pk[3]); }
         }
         if (l > 2) {
           fence_proxy_async();
@@ -524,6 +546,17 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
 
 using namespace sg;
 
+// bf16 [7][n][256] stash as a 3-D tensor map, box = one 128-row x 64-column operand tile
+static bool sdf_stash_map(CUtensorMap* m, const void* base, long long n) {
+  if (getenv("SG_B200_NO_TMA_STASH") != nullptr) return false;
+  if (n >= (1LL << 31) || ((uintptr_t)base & 15)) return false;
+  const uint64_t dims[3] = {256, (uint64_t)n, 7};
+  const uint64_t str[2] = {512, (uint64_t)n * 512};
+  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t one[3] = {1, 1, 1};
+  return tma_make_map(m, base, 3, dims, str, box, one);
+}
+
 extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   if (!a || !a->points || !a->latent || !a->w_img || !a->aux || !a->out) return sg_fail(-1, "sg_sdfnet_fwd: null");
   if (a->n <= 0) return 0;
@@ -534,6 +567,7 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   const long long tiles = (a->n + kTileRows - 1) / kTileRows;
   p.pairs = (tiles + 1) / 2;
   p.err = sg_error_word();
+  p.tma_stash = (p.stash != nullptr && sdf_stash_map(&p.tm_stash, p.stash, a->n)) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
@@ -566,6 +600,7 @@ extern "C" int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream) {
   const long long tiles = (a->n + kTileRows - 1) / kTileRows;
   p.pairs = (tiles + 1) / 2;
   p.err = sg_error_word();
+  p.tma_stash = sdf_stash_map(&p.tm_stash, p.gstash, a->n) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfBwdSmem);

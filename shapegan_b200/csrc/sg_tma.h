@@ -61,6 +61,17 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"((uint32_t)__cvta_generic_to_shared(bar))
       : "memory");
 }
+// shared -> global tile store (bulk async-group completion): the box is read from 128B-swizzled shared memory
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(m), "r"(c0), "r"(c1), "r"(c2),
+               "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed stores of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have been written out completely
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 #endif
 
 // Decomposition of a tile of `rows` consecutive (n, z, y, x) grid points (x fastest) into a box; needs power-of-two
