@@ -225,6 +225,9 @@ int sg_device_error_word(int32_t** dev_ptr); /* device word set by a kernel watc
 int sg_check_device_error(void);               /* diagnostic, synchronises: returns and clears that word */
 int sg_num_sms(void);
 long long sg_launch_count(void);               /* kernels launched by this library since load (bench gpu_launches) */
+/* diagnostics (tools/diag_conv.py): clock64 trace [3][1024] {producer got a stage, MMA warp got its data, MMAs issued} of CTA 0
+ * of the last sg_igemm launched with env SG_B200_IGEMM_DIAG & 128; synchronises */
+int sg_debug_igemm_trace(long long* host_out, int n);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,8 @@ constexpr int kProducerThreads = 128;
 constexpr int kIgemmThreads = 288;      // 4 producer warps + 1 MMA warp + 4 epilogue warps
 constexpr int kMaxStages = 6;
 constexpr int kSmemHeader = 2048;       // barriers + tmem pointer + staged bias
+constexpr int kTraceLen = 1024;
+__device__ long long g_igemm_trace[3 * kTraceLen];   // SG_B200_IGEMM_DIAG & 128: clock64 of CTA 0 {producer got slot, MMA got data, MMA issued}
 
 struct IgemmP {
   int mode, planes;
@@ -35,6 +37,8 @@ struct IgemmP {
   const bf16* mask; long long mask_ps; int mask_act;
   char* out; long long out_ps; int out_kind, out_ld, oD, oH, oW;
   int stages, m_tiles, n_tiles; long long work_total;
+  int diag;              // measurement only (SG_B200_IGEMM_DIAG): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip the epilogue stores,
+                         // 16 skip the whole K loop and epilogue (launch + prologue + teardown only)
   int acc_bufs, acc_slot;
   unsigned ktab_bytes, stage_bytes, a_stage_bytes;
   int* err;
@@ -131,7 +135,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
           __syncwarp();
           tmem_ld32(t_addr + c0, r);
           tmem_ld_wait();
-          if (!valid) continue;
+          if (!valid || (gp.diag & 8)) continue;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -254,15 +258,22 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
   }
 
   const int cps = (p.kchunks + p.ksplit - 1) / p.ksplit;   // K chunks per split
+  if (p.diag & 16) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    return;
+  }
 
   if (warp < 4 && p.use_tma) {
-    // ================================================================ TMA PRODUCER (one thread)
-    if (tid == 0) {
-      tma_prefetch_desc(&p.tmA[0]);
-      if (p.planes == 2) tma_prefetch_desc(&p.tmA[1]);
+    // ================================================================ TMA PRODUCER (warp 0; one elected lane issues)
+    if (warp == 0) {
+      if (elect_one()) {
+        tma_prefetch_desc(&p.tmA[0]);
+        if (p.planes == 2) tma_prefetch_desc(&p.tmA[1]);
+      }
       int s = 0; uint32_t ph = 0;
       const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
-      const uint32_t tx_bytes = p.a_stage_bytes + b_tile_bytes * p.planes;
       const int c1chunks = (p.aC + 63) >> 6;
       // power-of-two row grid: tile origin by shifts/masks, once per tile (no 64-bit division in the K loop)
       const int lgx = 31 - __clz(max(p.gx, 1)), lgy = 31 - __clz(max(p.gy, 1)), lgz = 31 - __clz(max(p.gz, 1));
@@ -287,28 +298,32 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
         const size_t bplane = (size_t)p.n_pad * 128;
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+          if ((p.diag & 128) && blockIdx.x == 0 && lane == 0 && kc - k0 < kTraceLen) g_igemm_trace[kc - k0] = clock64();
           uint64_t* bar = &hdr->full[s];
           const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
-          mbar_arrive_expect_tx(bar, tx_bytes);
           int ox = 0, oy = 0, oz = 0;
           if (p.mode == SG_MODE_CONV) { oz = (tap >> 4) - 1; oy = ((tap >> 2) & 3) - 1; ox = (tap & 3) - 1; }
           else if (p.mode == SG_MODE_CONVT) {
             const int td = (tap >> 2) & 1, th = (tap >> 1) & 1, tw = tap & 1;
             oz = pd ? 1 - td : -td; oy = phh ? 1 - th : -th; ox = pw ? 1 - tw : -tw;
           }
-          for (int sub = 0; sub < p.mt; ++sub) {
-            for (int pl = 0; pl < p.planes; ++pl) {
-              const uint32_t dst = a_base + (uint32_t)(sub * p.planes + pl) * kTileBytes;
-              if (p.mode == SG_MODE_DENSE) {
-                if (kc < c1chunks) tma_load_2d(dst, &p.tmA[pl], kc * 64, trow[sub], bar);
-                else tma_load_2d(dst, &p.tmA2[pl], (kc - c1chunks) * 64, trow[sub], bar);
-              } else {
-                tma_load_5d(dst, &p.tmA[pl], c0, tx0[sub] + ox, ty0[sub] + oy, tz0[sub] + oz, tn0[sub], bar);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar, ((p.diag & 1) ? 0u : p.a_stage_bytes) + ((p.diag & 2) ? 0u : b_tile_bytes * p.planes));
+            for (int sub = 0; sub < ((p.diag & 1) ? 0 : p.mt); ++sub) {
+              for (int pl = 0; pl < p.planes; ++pl) {
+                const uint32_t dst = a_base + (uint32_t)(sub * p.planes + pl) * kTileBytes;
+                if (p.mode == SG_MODE_DENSE) {
+                  if (kc < c1chunks) tma_load_2d(dst, &p.tmA[pl], kc * 64, trow[sub], bar);
+                  else tma_load_2d(dst, &p.tmA2[pl], (kc - c1chunks) * 64, trow[sub], bar);
+                } else {
+                  tma_load_5d(dst, &p.tmA[pl], c0, tx0[sub] + ox, ty0[sub] + oy, tz0[sub] + oz, tn0[sub], bar);
+                }
               }
             }
+            const uint32_t b_dst = a_base + p.a_stage_bytes;
+            for (int pl = 0; pl < ((p.diag & 2) ? 0 : p.planes); ++pl) bulk_g2s(b_dst + pl * b_tile_bytes, bsrc + pl * bplane, b_tile_bytes, bar);
           }
-          const uint32_t b_dst = a_base + p.a_stage_bytes;
-          for (int pl = 0; pl < p.planes; ++pl) bulk_g2s(b_dst + pl * b_tile_bytes, bsrc + pl * bplane, b_tile_bytes, bar);
+          __syncwarp();
           bsrc += (size_t)p.planes * bplane;
           c0 += 64;
           if (c0 >= p.aC) { c0 = 0; ++tap; }
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             }
           }
         }
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           mbar_arrive_expect_tx(&hdr->full[s], b_tile_bytes * p.planes);
           const uint32_t b_dst = a_base + p.a_stage_bytes;
           for (int pl = 0; pl < p.planes; ++pl) {
@@ -500,35 +515,51 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
       mbar_wait(&hdr->accempty[ab], aph ^ 1, p.err);
       tc_fence_after();
       const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
+      // The tensor pipe only queues a few MMAs: the barrier poll for the NEXT stage (a few hundred cycles of issue-thread time)
+      // is taken with the last K step of this stage still to issue, so the pipe never drains between stages.
+      auto issue = [&](int sub, int kk, int kc) {
+        const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
+        const uint32_t b_base = a_base + p.a_stage_bytes;
+        const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+        const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
+        const uint32_t a_hi = a_base + (uint32_t)(sub * p.planes) * kTileBytes;
+        const uint64_t da = umma_desc(a_hi + kk * 32, 16, 1024);
+        const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
+        umma_bf16(d_addr, da, db, idesc, (kc > k0 || kk > 0) ? 1u : 0u);
+        if (p.planes == 2) {
+          const uint64_t da_lo = umma_desc(a_hi + kTileBytes + kk * 32, 16, 1024);
+          const uint64_t db_lo = umma_desc(b_base + b_tile_bytes + kk * 32, 16, 1024);
+          umma_bf16(d_addr, da, db_lo, idesc, 1u);
+          umma_bf16(d_addr, da_lo, db, idesc, 1u);
+        }
+      };
+      mbar_wait(&hdr->full[s], ph, p.err);
+      tc_fence_after();
       for (int kc = k0; kc < k1; ++kc) {
-        mbar_wait(&hdr->full[s], ph, p.err);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
-          const uint32_t b_base = a_base + p.a_stage_bytes;
-          const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
-          for (int sub = 0; sub < p.mt; ++sub) {
-            const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
-            const uint32_t a_hi = a_base + (uint32_t)(sub * p.planes) * kTileBytes;
+        if ((p.diag & 128) && blockIdx.x == 0 && lane == 0 && kc - k0 < kTraceLen) g_igemm_trace[kTraceLen + kc - k0] = clock64();
+        const int mt_run = (p.diag & 4) ? 0 : p.mt;
+        if (elect_one()) {
+          for (int sub = 0; sub < mt_run; ++sub) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = umma_desc(a_hi + kk * 32, 16, 1024);
-              const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
-              umma_bf16(d_addr, da, db, idesc, (kc > k0 || kk > 0) ? 1u : 0u);
-              if (p.planes == 2) {
-                const uint64_t da_lo = umma_desc(a_hi + kTileBytes + kk * 32, 16, 1024);
-                const uint64_t db_lo = umma_desc(b_base + b_tile_bytes + kk * 32, 16, 1024);
-                umma_bf16(d_addr, da, db_lo, idesc, 1u);
-                umma_bf16(d_addr, da_lo, db, idesc, 1u);
-              }
-            }
+            for (int kk = 0; kk < 4; ++kk)
+              if (sub + 1 < mt_run || kk < 3) issue(sub, kk, kc);
           }
+        }
+        __syncwarp();
+        if (kc + 1 < k1) {               // next stage of this tile: poll its barrier under the MMAs queued above
+          const int sn = (s + 1 == S) ? 0 : s + 1;
+          mbar_wait(&hdr->full[sn], (sn == 0) ? (ph ^ 1u) : ph, p.err);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          if (mt_run > 0) issue(mt_run - 1, 3, kc);
           umma_commit(&hdr->empty[s]);
+          if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[2 * kTraceLen + kc - k0] = clock64();
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
       }
-      if (lane == 0) umma_commit(&hdr->accfull[ab]);
+      if (elect_one()) umma_commit(&hdr->accfull[ab]);
       __syncwarp();
     }
   } else {
@@ -694,10 +725,19 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
+  { const char* dg = getenv("SG_B200_IGEMM_DIAG"); p.diag = dg ? atoi(dg) : 0; }
   const int grid = (int)std::min<long long>(p.work_total, sms);
   sg_igemm_kernel<<<grid, kIgemmThreads, smem, (cudaStream_t)stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
   sg_count_launch();
+  return 0;
+}
+
+// diagnostics: clock64 trace of CTA 0 of the last sg_igemm launched with SG_B200_IGEMM_DIAG & 128 (synchronises)
+extern "C" int sg_debug_igemm_trace(long long* host_out, int n) {
+  if (!host_out || n <= 0 || n > 3 * kTraceLen) return sg_fail(-1, "sg_debug_igemm_trace: bad args");
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, g_igemm_trace, sizeof(long long) * (size_t)n, 0, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
   return 0;
 }

@@ -129,17 +129,18 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
 
   if (warp == 0) {
     // ================================================================ weight loader
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
-        for (int j = 0; j < kSdfStreamChunks; ++j, ++g) {
-          // stream position -> image chunk: [14,16) and [20,22) are the latent chunks 18,19 of layers2.0, [16,20) its hidden chunks 14-17
-          const int ic = j < 14 ? j : (j < 16 ? j + 4 : j - 2);
-          const uint32_t st = g & 1u;
-          mbar_wait(&hdr->w_empty[st], ((g >> 1) & 1u) ^ 1u, p.err);
+    uint32_t g = 0;
+    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+      for (int j = 0; j < kSdfStreamChunks; ++j, ++g) {
+        // stream position -> image chunk: [14,16) and [20,22) are the latent chunks 18,19 of layers2.0, [16,20) its hidden chunks 14-17
+        const int ic = j < 14 ? j : (j < 16 ? j + 4 : j - 2);
+        const uint32_t st = g & 1u;
+        mbar_wait(&hdr->w_empty[st], ((g >> 1) & 1u) ^ 1u, p.err);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&hdr->w_full[st], kChunkBytes);
           bulk_g2s(s_base + kOffW + st * kChunkBytes, p.w_img + (size_t)ic * kChunkBytes, kChunkBytes, &hdr->w_full[st]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
     auto latent_mma = [&](int t, bool commit_acc) {
       mbar_wait(&hdr->lat_full, lat_n & 1u, p.err); ++lat_n;
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)t * 256u;
         for (int c = 0; c < 2; ++c) {
           const uint32_t a = s_base + kOffLat + c * kTileBytes, b = s_base + kOffW + ((g + c) & 1u) * kChunkBytes;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
       mbar_wait(&hdr->w_full[(g + 1) & 1u], ((g + 1) >> 1) & 1u, p.err);
     };
     auto release_two_chunks = [&]() {
-      if (lane == 0) { umma_commit(&hdr->w_empty[g & 1u]); umma_commit(&hdr->w_empty[(g + 1) & 1u]); }
+      if (elect_one()) { umma_commit(&hdr->w_empty[g & 1u]); umma_commit(&hdr->w_empty[(g + 1) & 1u]); }
       __syncwarp();
       g += 2;
     };
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         // h[t] holds the activations of layer l-1 and accumulator t is drained and re-initialised
         for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }
         tc_fence_after();
-        if (p.tma_stash && l >= 2 && lane == 0) {      // h_{l-1} of both tiles: SMEM tiles -> stash[l-2] (rows >= n are clipped)
+        if (p.tma_stash && l >= 2 && elect_one()) {      // h_{l-1} of both tiles: SMEM tiles -> stash[l-2] (rows >= n are clipped)
           for (int t = 0; t < 2; ++t)
             for (int c = 0; c < 4; ++c)
               tma_store_3d(&p.tm_stash, s_base + (t ? kOffHB : kOffHA) + c * kTileBytes, c * 64, (int)((pr * 2 + t) * kTileRows), l - 2);
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         for (int c = 0; c < 4; ++c, ++g) {
           mbar_wait(&hdr->w_full[g & 1u], (g >> 1) & 1u, p.err);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t b = s_base + kOffW + (g & 1u) * kChunkBytes;
             for (int t = 0; t < 2; ++t) {
               const uint32_t d = tmem_base + (uint32_t)t * 256u;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         }
       }
     }
-    if (p.tma_stash && lane == 0) tma_store_wait_all();
+    if (p.tma_stash && elect_one()) tma_store_wait_all();
   } else if (warp >= 2 && warp < 6) {
     // ================================================================ latent gather: fp32 table rows -> bf16 swizzled A tile
     const int gw = warp - 2;
@@ -392,15 +393,16 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
 
   if (warp == 0) {
     // ================================================================ weight loader
-    if (lane == 0) {
-      uint32_t st = 0, ph = 0;
-      for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
-        for (int j = 0; j < kSdfBwdChunks; ++j) {
-          mbar_wait(&hdr->w_empty[st], ph ^ 1u, p.err);
+    uint32_t st = 0, ph = 0;
+    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+      for (int j = 0; j < kSdfBwdChunks; ++j) {
+        mbar_wait(&hdr->w_empty[st], ph ^ 1u, p.err);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&hdr->w_full[st], kChunkBytes);
           bulk_g2s(s_base + kOffBW + st * kChunkBytes, p.wt_img + (size_t)j * kChunkBytes, kChunkBytes, &hdr->w_full[st]);
-          if (++st == kSdfBwdStages) { st = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++st == kSdfBwdStages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
       for (int l = 7; l >= 2; --l) {
         for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }   // g_l in SMEM, accumulator drained
         tc_fence_after();
-        if (p.tma_stash && lane == 0) {               // g_l of both tiles: SMEM operand tiles -> gstash[l-1] (rows >= n are clipped)
+        if (p.tma_stash && elect_one()) {             // g_l of both tiles: SMEM operand tiles -> gstash[l-1] (rows >= n are clipped)
           for (int t = 0; t < 2; ++t)
             for (int c = 0; c < 4; ++c)
               tma_store_3d(&p.tm_stash, s_base + (t ? kOffHB : kOffHA) + c * kTileBytes, c * 64, (int)((pr * 2 + t) * kTileRows), l - 1);
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
         for (int c = 0; c < 4; ++c) {
           mbar_wait(&hdr->w_full[st], ph, p.err);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t b = s_base + kOffBW + st * kChunkBytes;
             for (int t = 0; t < 2; ++t) {
               const uint32_t d = tmem_base + (uint32_t)t * 256u;
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
         }
       }
     }
-    if (p.tma_stash && lane == 0) tma_store_wait_all();
+    if (p.tma_stash && elect_one()) tma_store_wait_all();
   } else if (warp >= 2) {
     // ================================================================ epilogue: tile t, lane quadrant q (32 rows), column half
     const int e = warp - 2;

@@ -66,10 +66,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
   const int rpi = p.rs / 16;                                   // rows handled per producer thread per atom
 
   if (warp < 4 && p.use_tma) {
-    // ================================================================ TMA PRODUCER (one thread): every atom is one box
-    if (tid == 0) {
-      tma_prefetch_desc(&p.tmA[0]);
-      tma_prefetch_desc(&p.tmB[0]);
+    // ================================================================ TMA PRODUCER (warp 0, one elected lane issues): every atom is one box
+    if (warp == 0) {
+      if (elect_one()) {
+        tma_prefetch_desc(&p.tmA[0]);
+        tma_prefetch_desc(&p.tmB[0]);
+      }
       int s = 0; uint32_t ph = 0;
       const int lgx = 31 - __clz(max(p.gx, 1)), lgy = 31 - __clz(max(p.gy, 1)), lgz = 31 - __clz(max(p.gz, 1));
       for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
@@ -91,11 +93,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
           mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
           uint64_t* bar = &hdr->full[s];
           const uint32_t base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
-          mbar_arrive_expect_tx(bar, tx_bytes);
           const uint32_t row0 = (uint32_t)rt * (uint32_t)p.rs;
-          for (int at = 0; at < kAtomsA; ++at)
-            for (int pl = 0; pl < p.planes; ++pl)
-              tma_load_2d(base + (uint32_t)(at * p.planes + pl) * p.tile_bytes, &p.tmA[pl], m0 + at * 64, (int)row0, bar);
           const uint32_t bbase = base + (uint32_t)(kAtomsA * p.planes) * p.tile_bytes;
           int x0 = 0, y0 = 0, z0 = 0, n0 = 0;
           if (p.b_mode == SG_MODE_CONV) {
@@ -104,13 +102,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
             z0 = 2 * (int)((row0 >> (lgx + lgy)) & (uint32_t)(p.gz - 1));
             n0 = (int)(row0 >> (lgx + lgy + lgz));
           }
-          for (int j = 0; j < nb_atoms; ++j) {
-            for (int pl = 0; pl < p.planes; ++pl) {
-              const uint32_t dst = bbase + (uint32_t)(j * p.planes + pl) * p.tile_bytes;
-              if (p.b_mode == SG_MODE_DENSE) tma_load_2d(dst, &p.tmB[pl], bcb[j], (int)row0, bar);
-              else tma_load_5d(dst, &p.tmB[pl], bcb[j], x0 + bkx[j], y0 + bky[j], z0 + bkz[j], n0, bar);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar, tx_bytes);
+            for (int at = 0; at < kAtomsA; ++at)
+              for (int pl = 0; pl < p.planes; ++pl)
+                tma_load_2d(base + (uint32_t)(at * p.planes + pl) * p.tile_bytes, &p.tmA[pl], m0 + at * 64, (int)row0, bar);
+            for (int j = 0; j < nb_atoms; ++j) {
+              for (int pl = 0; pl < p.planes; ++pl) {
+                const uint32_t dst = bbase + (uint32_t)(j * p.planes + pl) * p.tile_bytes;
+                if (p.b_mode == SG_MODE_DENSE) tma_load_2d(dst, &p.tmB[pl], bcb[j], (int)row0, bar);
+                else tma_load_5d(dst, &p.tmB[pl], bcb[j], x0 + bkx[j], y0 + bky[j], z0 + bkz[j], n0, bar);
+              }
             }
           }
+          __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
       for (int rt = t0; rt < t1; ++rt) {
         mbar_wait(&hdr->full[s], ph, p.err);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
           const uint32_t b_base = a_base + (uint32_t)(kAtomsA * p.planes) * p.tile_bytes;
           const int ksteps = p.rs / 16;
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
       }
-      if (lane == 0) umma_commit(&hdr->accfull[ab]);
+      if (elect_one()) umma_commit(&hdr->accfull[ab]);
       __syncwarp();
     }
   } else {

@@ -100,7 +100,11 @@ class WGANStep:
         self.gopt.zero_grad(); self.copt.zero_grad()                    # train_wgan.py:62-63
         with torch.no_grad():
             fake = gen(z_critic)                                       # .detach() at :65: no graph is needed
-        closs = torch.mean(cri(fake)) - torch.mean(cri(real))          # :66-68
+        # :66-68  critic(fake) and critic(valid) as ONE batch of 2B samples: the critic has no BatchNorm (model/gan.py:48-57), so the
+        # samples are independent and mean(D(fake)) - mean(D(real)) and every gradient are the same sums, in half the launches
+        b = real.shape[0]
+        score = cri(torch.cat((fake.reshape(real.shape), real), 0))
+        closs = torch.mean(score[:b]) - torch.mean(score[b:])
         if self.gp:
             closs = closs + gradient_penalty(cri, real, fake.squeeze(1), alpha, self.gp_weight)
         closs.backward()                                               # :69
@@ -213,7 +217,9 @@ class HybridProgressiveStep:
         self.gopt.zero_grad(); self.dopt.zero_grad()                                    # :153
         with torch.no_grad():                            # the reference back-propagates into G here and discards it (:136)
             fake = self.generate(z)
-        out_fake, out_valid = self.dis(fake), self.dis(valid)                          # :157,160
+        b = valid.shape[0]                               # one batch of 2B samples (no BatchNorm in the critic: same sums, half the launches)
+        out = self.dis(torch.cat((fake, valid), 0))                                    # :157,160
+        out_fake, out_valid = out[:b], out[b:]
         gp = gradient_penalty(self.dis, valid, fake, alpha, self.gp_weight)            # :162
         loss = out_fake.mean() - out_valid.mean() + gp                                 # :163
         loss.backward()

@@ -4,7 +4,8 @@ import csv, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout.splitlines()
 start = next(i for i, l in enumerate(raw) if l.startswith('"Address"'))
-rows = list(csv.DictReader(raw[start:]))
+ends = [i for i, l in enumerate(raw) if i > start and l.startswith('"Kernel Name"')]
+rows = list(csv.DictReader(raw[start:(ends[0] if ends else len(raw))]))      # first kernel of the report
 stalls = [k for k in rows[0] if k.startswith('stall_') and 'Not Issued' not in k]
 tot = sum(int(r['# Samples'] or 0) for r in rows)
 print('total samples', tot, 'instructions', len(rows))
