@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   uint32_t* ktab = reinterpret_cast<uint32_t*>(smem + kSmemHeader);
   uint8_t* stage0 = smem + kSmemHeader + p.ktab_bytes;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int S = p.stages;
 
   // ---------------------------------------------------------------- one-time setup
@@ -266,12 +266,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
   }
 
   if (warp < 4 && p.use_tma) {
-    // ================================================================ TMA PRODUCER (warp 0; one elected lane issues)
-    if (warp == 0) {
-      if (elect_one()) {
-        tma_prefetch_desc(&p.tmA[0]);
-        if (p.planes == 2) tma_prefetch_desc(&p.tmA[1]);
-      }
+    // ================================================================ TMA PRODUCER: ONE elected thread runs the whole loop (waits
+    // included): no per-stage elect / warp re-convergence on the issue path
+    if (warp == 0 && elect_one()) {
+      tma_prefetch_desc(&p.tmA[0]);
+      if (p.planes == 2) tma_prefetch_desc(&p.tmA[1]);
       int s = 0; uint32_t ph = 0;
       const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
       const int c1chunks = (p.aC + 63) >> 6;
@@ -298,7 +297,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
         const size_t bplane = (size_t)p.n_pad * 128;
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
-          if ((p.diag & 128) && blockIdx.x == 0 && lane == 0 && kc - k0 < kTraceLen) g_igemm_trace[kc - k0] = clock64();
+          if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[kc - k0] = clock64();
           uint64_t* bar = &hdr->full[s];
           const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
           int ox = 0, oy = 0, oz = 0;
@@ -307,7 +306,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             const int td = (tap >> 2) & 1, th = (tap >> 1) & 1, tw = tap & 1;
             oz = pd ? 1 - td : -td; oy = phh ? 1 - th : -th; ox = pw ? 1 - tw : -tw;
           }
-          if (elect_one()) {
+          {
             mbar_arrive_expect_tx(bar, ((p.diag & 1) ? 0u : p.a_stage_bytes) + ((p.diag & 2) ? 0u : b_tile_bytes * p.planes));
             for (int sub = 0; sub < ((p.diag & 1) ? 0 : p.mt); ++sub) {
               for (int pl = 0; pl < p.planes; ++pl) {
@@ -323,7 +322,6 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             const uint32_t b_dst = a_base + p.a_stage_bytes;
             for (int pl = 0; pl < ((p.diag & 2) ? 0 : p.planes); ++pl) bulk_g2s(b_dst + pl * b_tile_bytes, bsrc + pl * bplane, b_tile_bytes, bar);
           }
-          __syncwarp();
           bsrc += (size_t)p.planes * bplane;
           c0 += 64;
           if (c0 >= p.aC) { c0 = 0; ++tap; }
@@ -505,8 +503,10 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     }
   } else if (warp == 4) {
     // ================================================================ MMA ISSUER
+    // ONE elected thread runs the whole loop (barrier polls included)
     const uint32_t idesc = umma_idesc(128, p.bn, false, false);
     int s = 0; uint32_t ph = 0; int it = 0;
+    if (elect_one())
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
       int cls, nt, mtile, ks;
       decode_work(p, w, cls, nt, mtile, ks);
@@ -515,53 +515,38 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
       mbar_wait(&hdr->accempty[ab], aph ^ 1, p.err);
       tc_fence_after();
       const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
-      // The tensor pipe only queues a few MMAs: the barrier poll for the NEXT stage (a few hundred cycles of issue-thread time)
-      // is taken with the last K step of this stage still to issue, so the pipe never drains between stages.
-      auto issue = [&](int sub, int kk, int kc) {
-        const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
-        const uint32_t b_base = a_base + p.a_stage_bytes;
-        const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
-        const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
-        const uint32_t a_hi = a_base + (uint32_t)(sub * p.planes) * kTileBytes;
-        const uint64_t da = umma_desc(a_hi + kk * 32, 16, 1024);
-        const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
-        umma_bf16(d_addr, da, db, idesc, (kc > k0 || kk > 0) ? 1u : 0u);
-        if (p.planes == 2) {
-          const uint64_t da_lo = umma_desc(a_hi + kTileBytes + kk * 32, 16, 1024);
-          const uint64_t db_lo = umma_desc(b_base + b_tile_bytes + kk * 32, 16, 1024);
-          umma_bf16(d_addr, da, db_lo, idesc, 1u);
-          umma_bf16(d_addr, da_lo, db, idesc, 1u);
-        }
-      };
-      mbar_wait(&hdr->full[s], ph, p.err);
-      tc_fence_after();
       for (int kc = k0; kc < k1; ++kc) {
-        if ((p.diag & 128) && blockIdx.x == 0 && lane == 0 && kc - k0 < kTraceLen) g_igemm_trace[kTraceLen + kc - k0] = clock64();
-        const int mt_run = (p.diag & 4) ? 0 : p.mt;
-        if (elect_one()) {
-          for (int sub = 0; sub < mt_run; ++sub) {
+        mbar_wait(&hdr->full[s], ph, p.err);
+        tc_fence_after();
+        if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[kTraceLen + kc - k0] = clock64();
+        {
+          const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
+          const uint32_t b_base = a_base + p.a_stage_bytes;
+          const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+          for (int sub = 0; sub < ((p.diag & 4) ? 0 : p.mt); ++sub) {
+            const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
+            const uint32_t a_hi = a_base + (uint32_t)(sub * p.planes) * kTileBytes;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              if (sub + 1 < mt_run || kk < 3) issue(sub, kk, kc);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = umma_desc(a_hi + kk * 32, 16, 1024);
+              const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
+              umma_bf16(d_addr, da, db, idesc, (kc > k0 || kk > 0) ? 1u : 0u);
+              if (p.planes == 2) {
+                const uint64_t da_lo = umma_desc(a_hi + kTileBytes + kk * 32, 16, 1024);
+                const uint64_t db_lo = umma_desc(b_base + b_tile_bytes + kk * 32, 16, 1024);
+                umma_bf16(d_addr, da, db_lo, idesc, 1u);
+                umma_bf16(d_addr, da_lo, db, idesc, 1u);
+              }
+            }
           }
-        }
-        __syncwarp();
-        if (kc + 1 < k1) {               // next stage of this tile: poll its barrier under the MMAs queued above
-          const int sn = (s + 1 == S) ? 0 : s + 1;
-          mbar_wait(&hdr->full[sn], (sn == 0) ? (ph ^ 1u) : ph, p.err);
-          tc_fence_after();
-        }
-        if (elect_one()) {
-          if (mt_run > 0) issue(mt_run - 1, 3, kc);
           umma_commit(&hdr->empty[s]);
           if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[2 * kTraceLen + kc - k0] = clock64();
         }
-        __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
       }
-      if (elect_one()) umma_commit(&hdr->accfull[ab]);
-      __syncwarp();
+      umma_commit(&hdr->accfull[ab]);
     }
+    __syncwarp();
   } else {
     // ================================================================ EPILOGUE
     switch (p.act) {
@@ -726,7 +711,8 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     attr_set = true;
   }
   { const char* dg = getenv("SG_B200_IGEMM_DIAG"); p.diag = dg ? atoi(dg) : 0; }
-  const int grid = (int)std::min<long long>(p.work_total, sms);
+  int grid = (int)std::min<long long>(p.work_total, sms);
+  { const char* gg = getenv("SG_B200_IGEMM_GRID"); if (gg && atoi(gg) > 0) grid = std::min(grid, atoi(gg)); }   // measurement only
   sg_igemm_kernel<<<grid, kIgemmThreads, smem, (cudaStream_t)stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));

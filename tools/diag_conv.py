@@ -48,13 +48,13 @@ for name, (fn, fl) in layers:
         os.environ['SG_B200_IGEMM_DIAG'] = str(d)
         us = timeit(fn)
         print('   diag=%2d %-12s %8.1f us  %7.1f TFLOP/s-equivalent' % (d, what, us, fl / us / 1e6))
-os.environ['SG_B200_IGEMM_DIAG'] = '0'
+os.environ['SG_B200_IGEMM_DIAG'] = '0'; os.environ['SG_B200_IGEMM_GRID'] = '0'
 
 # ---- per-iteration clock trace of CTA 0 (conv 64->128): where does a K-chunk iteration spend its time?
 import ctypes
 fn, _ = conv_fwd(16, 64, 128)
-for d, what in ((128, 'full'), (128 + 15, 'nothing'), (128 + 3, 'no loads'), (128 + 4, 'no MMA')):
-    os.environ['SG_B200_IGEMM_DIAG'] = str(d)
+for d, what, grid in ((128, 'full', 0), (128 + 15, 'nothing', 0), (128 + 3, 'no loads', 0), (128 + 4, 'no MMA', 0), (128 + 4, 'no MMA, 64 CTAs', 64), (128 + 4, 'no MMA, 32 CTAs', 32), (128 + 4, 'no MMA, 8 CTAs', 8), (128, 'full, 64 CTAs', 64)):
+    os.environ['SG_B200_IGEMM_DIAG'] = str(d); os.environ['SG_B200_IGEMM_GRID'] = str(grid)
     fn(); torch.cuda.synchronize(); flush.zero_(); fn(); torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 3072)()
     L.check(L.lib().sg_debug_igemm_trace(buf, 3072), 'trace')
@@ -64,4 +64,4 @@ for d, what in ((128, 'full'), (128 + 15, 'nothing'), (128 + 3, 'no loads'), (12
     for i in range(64):
         if i < 12 or i % 8 == 0 or i > 60:
             print('   %2d  %7d %7d %7d   +%d' % (i, prod[i] - t0, got[i] - t0, iss[i] - t0, iss[i] - iss[i - 1] if i else 0))
-os.environ['SG_B200_IGEMM_DIAG'] = '0'
+os.environ['SG_B200_IGEMM_DIAG'] = '0'; os.environ['SG_B200_IGEMM_GRID'] = '0'
