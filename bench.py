@@ -254,8 +254,59 @@ def roofline_probe(flush):
     pk, src = peaks()
     achieved = FLOPS_D2_FWD / (avg * 1e-3) / 1e12
     return {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops'],
-            'traffic': None, 'kernel': 'sg_igemm_kernel MODE_CONV Conv3d(64->128,k4,s2,p1) fwd B=64 (34.36 GFLOP/launch)',
-            'launch_ms': avg, 'peak_source': src + ', burst (kernel timed alone)'}
+            'traffic': 34.72e6, 'traffic_source': 'dram__bytes_read+write per launch, ncu --set full (profiles/r01g_ncu_prof_conv.txt); '
+            'algorithmic DRAM bytes 33.6 MB input + 1.0 MB weights (the 8.4 MB output stays in L2)',
+            'kernel': 'sg_igemm_kernel MODE_CONV Conv3d(64->128,k4,s2,p1) fwd B=64 (34.36 GFLOP/launch)',
+            'launch_ms': avg, 'peak_source': src + ', burst (kernel timed alone)',
+            'note': 'measured per-SM ceilings for this tile shape (tools/diag_conv.py, DESIGN.md 4): TMA ingest ~47 B/clk/SM, '
+                    'SS-mode 128x128x16 MMA ~108 clk (operand reads out of shared memory), i.e. shared-memory bandwidth, not L2 or HBM'}
+
+
+def sdfnet_probe(dev, world):
+    """SDFNet Mpoints/s (BASELINE.json metric, second half): fused forward at the north_star's 250k-point batch and at configs[2]'s
+    8.39 M points, plus the configs[2] autodecoder step.  Inputs exceed L2 at the large size; CUDA events, 3 warm-ups."""
+    from model.sdf_net import SDFNet
+    from shapegan_b200 import train
+    torch.manual_seed(0)
+    net = SDFNet()
+    pk, src = peaks()
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for tag, n, reps in (('fwd_250k_points', 250000, 20), ('fwd_8388608_points', 512 * 16384, 5)):
+        pts = torch.rand((n, 3), device=dev) * 2 - 1
+        table = torch.randn((512, 128), device=dev) * 0.1
+        idx = ((torch.arange(n, device=dev) * 512) // n).to(torch.int32)
+        with torch.no_grad():
+            ms = timed(lambda: net(pts, table, idx), reps)
+        tf = 0.921e6 * n / (ms * 1e-3) / 1e12
+        out[tag] = {'mpoints_per_s': n / ms / 1e3, 'ms': ms, 'tflops': tf, 'frac_of_burst_peak': tf / pk['bf16_tflops']}
+    n = 512 * 16384
+    pts = torch.rand((n, 3), device=dev) * 2 - 1
+    sdf = torch.clamp(pts.norm(dim=1) - 0.5, -0.1, 0.1)
+    idx = (torch.arange(n, device=dev) // 16384).to(torch.int32)
+    step = train.AutodecoderStep(net, torch.randn((512, 128), device=dev) * 0.01, world_size=1)
+    ms = timed(lambda: step(pts, sdf, idx), 5)
+    tf = 2.763e6 * n / (ms * 1e-3) / 1e12
+    out['autodecoder_step_512x16384'] = {'mpoints_per_s': n / ms / 1e3, 'ms': ms, 'tflops': tf, 'frac_of_sustained_peak': tf / pk['bf16_tflops_sustained']}
+    big = out['fwd_8388608_points']
+    out['roofline'] = {'bound': 'tensor', 'achieved': big['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': big['frac_of_burst_peak'],
+                       'traffic': 17.8e6 * 8, 'traffic_source': 'ncu dram bytes at 1 M points x 8 (profiles/r01g_ncu_prof_sdf.txt); algorithmic 16 B/point',
+                       'kernel': 'sg_sdfnet_fwd_kernel, 0.921 MFLOP/point (SURVEY 8d)', 'peak_source': src + ', burst'}
+    del step
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------- main arm
@@ -270,6 +321,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32x'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sdfnet', action='store_true', help='skip the secondary SDFNet Mpoints/s block')
     ap.add_argument('--ad-shapes', type=int, default=512, help='autodecoder workload: number of shapes (16384 points each)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -386,6 +438,11 @@ def main():
         'roofline': roof, 'clocks': clocks, 'device_error_word': err,
         'losses': [float(h_loss[0]), float(h_loss[1])],
     }
+    if not args.no_sdfnet:
+        try:
+            out['sdfnet'] = sdfnet_probe(dev, world)
+        except Exception as e:            # secondary numbers must never cost the headline line
+            out['sdfnet'] = {'error': str(e).split('\n')[0][:200]}
     if not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(args.workload)
     print(json.dumps(out))

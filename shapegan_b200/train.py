@@ -162,13 +162,18 @@ class AutodecoderStep:
         self.table = latent_table.detach().clone().requires_grad_(True)
         self.nopt = FlatOptimizer(sdf_net.parameters(), 'adam', lr, world_size=world_size)
         self.lopt = FlatOptimizer([self.table], 'adam', lr, world_size=world_size)
+        self._counts_key, self._counts = None, None
 
     def __call__(self, points, sdf, shape_index):
         """points [N,3], sdf [N], shape_index int32 [N] (= point_index // POINTCLOUD_SIZE, :78 with the D6 fix)."""
         self.nopt.zero_grad(); self.lopt.zero_grad()                    # :84-86
         out = self.net(points, self.table, shape_index)                # :80,87 without materialising table[index]
         # mean(z_batch^2) over the gathered rows == sum_s count_s*|table_s|^2 / (N*L): [S,L] math instead of [N,L]
-        counts = torch.bincount(shape_index, minlength=self.table.shape[0]).to(torch.float32)
+        key = (shape_index.data_ptr(), shape_index._version, shape_index.numel())
+        if self._counts_key != key:                      # points per shape: recomputed only when the index tensor changes
+            self._counts = torch.bincount(shape_index, minlength=self.table.shape[0]).to(torch.float32)
+            self._counts_key = key
+        counts = self._counts
         reg = (counts.unsqueeze(1) * torch.pow(self.table, 2)).sum() / (points.shape[0] * self.table.shape[1])
         loss = torch.mean(torch.abs(out - sdf)) + self.sigma * reg     # :88
         loss.backward()                                                # :89
