@@ -55,7 +55,7 @@ class ClockSampler(threading.Thread):
         self.index, self.stop_flag, self.rows = index, False, []
         q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        self.cmd = ['nvidia-smi', '-i', str(index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '200']
+        self.cmd = ['nvidia-smi', '-i', str(index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '25']
         self.proc = None
 
     def run(self):
