@@ -21,6 +21,7 @@
 namespace sg {
 
 constexpr int kProducerThreads = 128;
+constexpr int kBLoaderThreads = 96;    // TMA mode: warps 1-3 stream the weight tile with cp.async (keeps it off the TMA unit)
 constexpr int kIgemmThreads = 288;      // 4 producer warps + 1 MMA warp + 4 epilogue warps
 constexpr int kMaxStages = 6;
 constexpr int kSmemHeader = 2048;       // barriers + tmem pointer + staged bias
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], p.use_tma ? 1 : kProducerThreads + 1); mbar_init(&hdr->empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], (p.use_tma ? kBLoaderThreads : kProducerThreads) + 1); mbar_init(&hdr->empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128); }
     fence_mbar_init();
   }
@@ -272,7 +273,6 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
       tma_prefetch_desc(&p.tmA[0]);
       if (p.planes == 2) tma_prefetch_desc(&p.tmA[1]);
       int s = 0; uint32_t ph = 0;
-      const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
       const int c1chunks = (p.aC + 63) >> 6;
       // power-of-two row grid: tile origin by shifts/masks, once per tile (no 64-bit division in the K loop)
       const int lgx = 31 - __clz(max(p.gx, 1)), lgy = 31 - __clz(max(p.gy, 1)), lgz = 31 - __clz(max(p.gz, 1));
@@ -293,8 +293,6 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
         }
         int tap = 0, c0 = 0;
         if (p.mode != SG_MODE_DENSE) { tap = (k0 * 64) / p.aC; c0 = k0 * 64 - tap * p.aC; }
-        const char* bsrc = p.b + (((size_t)cls * p.kchunks + k0) * p.planes * p.n_pad + (size_t)nt * p.bn) * 128;
-        const size_t bplane = (size_t)p.n_pad * 128;
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
           if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[kc - k0] = clock64();
@@ -307,7 +305,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             oz = pd ? 1 - td : -td; oy = phh ? 1 - th : -th; ox = pw ? 1 - tw : -tw;
           }
           {
-            mbar_arrive_expect_tx(bar, ((p.diag & 1) ? 0u : p.a_stage_bytes) + ((p.diag & 2) ? 0u : b_tile_bytes * p.planes));
+            mbar_arrive_expect_tx(bar, (p.diag & 1) ? 0u : p.a_stage_bytes);
             for (int sub = 0; sub < ((p.diag & 1) ? 0 : p.mt); ++sub) {
               for (int pl = 0; pl < p.planes; ++pl) {
                 const uint32_t dst = a_base + (uint32_t)(sub * p.planes + pl) * kTileBytes;
@@ -319,14 +317,57 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
                 }
               }
             }
-            const uint32_t b_dst = a_base + p.a_stage_bytes;
-            for (int pl = 0; pl < ((p.diag & 2) ? 0 : p.planes); ++pl) bulk_g2s(b_dst + pl * b_tile_bytes, bsrc + pl * bplane, b_tile_bytes, bar);
           }
-          bsrc += (size_t)p.planes * bplane;
           c0 += 64;
           if (c0 >= p.aC) { c0 = 0; ++tap; }
           if (++s == S) { s = 0; ph ^= 1; }
         }
+      }
+    }
+    // ================================================================ WEIGHT-TILE LOADERS (warps 1-3): the packed B tile of every stage
+    // is a linear copy; moving it with 16-byte cp.async (LSU path) instead of a bulk copy leaves the TMA unit -- this kernel's
+    // per-SM load limit, ~3.5 clk per gathered 128-byte row -- to the A tiles alone (loads-only 48 -> 44 us on Conv3d 64->128).
+    // Gathering A rows this way as well was measured 3x slower than TMA.  Completion: wait_group (one stage behind),
+    // generic->async proxy fence, arrive.
+    if (warp >= 1) {
+      const int bt = tid - 32;                                   // 0..95
+      int s = 0; uint32_t ph = 0;
+      int pending = 0, oldest = 0;
+      const uint32_t pieces = (uint32_t)p.planes * (uint32_t)p.bn * 8u;      // 16-byte pieces per stage
+      const size_t bplane = (size_t)p.n_pad * 128;
+      for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+        int cls, nt, mtile, ks;
+        decode_work(p, w, cls, nt, mtile, ks);
+        const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
+        const char* bsrc = p.b + (((size_t)cls * p.kchunks + k0) * p.planes * p.n_pad + (size_t)nt * p.bn) * 128;
+        for (int kc = k0; kc < k1; ++kc) {
+          mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+          const uint32_t b_dst = smem_u32(stage0 + (size_t)s * p.stage_bytes) + p.a_stage_bytes;
+          if (!(p.diag & 2)) {
+            if (p.planes == 1) {
+              for (uint32_t i = (uint32_t)bt; i < pieces; i += kBLoaderThreads) cp_async16(b_dst + i * 16u, bsrc + (size_t)i * 16u, 16u);
+            } else {
+              const uint32_t per_plane = (uint32_t)p.bn * 8u;
+              for (uint32_t i = (uint32_t)bt; i < pieces; i += kBLoaderThreads) {
+                const uint32_t pl = i / per_plane, j = i - pl * per_plane;
+                cp_async16(b_dst + i * 16u, bsrc + pl * bplane + (size_t)j * 16u, 16u);
+              }
+            }
+          }
+          cp_async_commit();
+          if (++pending > 1) {
+            cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+            if (++oldest == S) oldest = 0;
+            --pending;
+          }
+          bsrc += (size_t)p.planes * bplane;
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+      while (pending > 0) {
+        cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+        if (++oldest == S) oldest = 0;
+        --pending;
       }
     }
   } else if (warp < 4) {

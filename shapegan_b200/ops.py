@@ -305,9 +305,11 @@ def linear_op(in_f, out_f, tag='lin'):
 
 
 # ------------------------------------------------------------------------------------------------- generic Functions
-def _bias_grad(g, c):
-    """column sums of a plane tensor viewed as [rows, c] -> fp32 [c]"""
+def _bias_grad(g, c, into=None):
+    """column sums of a plane tensor viewed as [rows, c] -> fp32 [c] (accumulated into `into` when given)"""
     _, sums = raw.act_bwd(g, None, ACT_NONE, c, want_sums=True, want_g=False)
+    if into is not None:
+        return raw.emit_sums(sums, into, c, accumulate=True)
     out = torch.empty(c, dtype=torch.float32, device=g.device)
     return raw.emit_sums(sums, out, c)
 
@@ -318,20 +320,24 @@ class _MaskMul(Function):
     gradient), returned as a non-differentiable second output."""
 
     @staticmethod
-    def forward(ctx, ga, y, act, c, want_bias):
+    def forward(ctx, ga, y, act, c, want_bias, bias_into=None):
         ctx.act, ctx.c = act, c
         ctx.save_for_backward(y)
         g, sums = raw.act_bwd(ga.contiguous(), y, act, c, want_sums=want_bias)
-        gb = torch.empty(c if want_bias else 0, dtype=torch.float32, device=ga.device)
-        if want_bias:
-            raw.emit_sums(sums, gb, c)
+        if want_bias and bias_into is not None:       # accumulate straight into an allocated .grad (flat gradient arena)
+            raw.emit_sums(sums, bias_into, c, accumulate=True)
+            gb = torch.empty(0, dtype=torch.float32, device=ga.device)
+        else:
+            gb = torch.empty(c if want_bias else 0, dtype=torch.float32, device=ga.device)
+            if want_bias:
+                raw.emit_sums(sums, gb, c)
         ctx.mark_non_differentiable(gb)
         return g, gb
 
     @staticmethod
     def backward(ctx, gg, _ggb):
         (y,) = ctx.saved_tensors
-        return _MaskMul.apply(gg, y, ctx.act, ctx.c, False)[0], None, None, None, None
+        return _MaskMul.apply(gg, y, ctx.act, ctx.c, False)[0], None, None, None, None, None
 
 
 class _Fwd(Function):
@@ -342,6 +348,7 @@ class _Fwd(Function):
         x = x.contiguous()
         y = op.fwd(x, w, bias, act)
         ctx.op, ctx.act, ctx.has_bias = op, act, bias is not None
+        ctx.bias_obj = bias
         ctx.w_obj = w                       # identity for the pack cache; saved_tensors still does the version check
         ctx.save_for_backward(x, w, y)
         return y
@@ -355,8 +362,14 @@ class _Fwd(Function):
         c = op.out_channels()
         want_b = ctx.has_bias and ctx.needs_input_grad[3]
         gb_fused = None
+        # first-order backward with an allocated bias .grad (flat gradient arena): the bias sums accumulate in place, like the
+        # weight gradient below -- no temporary, no AccumulateGrad add kernel
+        b_into = None
+        if want_b and (not torch.is_grad_enabled()) and ctx.bias_obj.grad is not None and ctx.bias_obj.grad.is_contiguous() \
+                and ctx.bias_obj.grad.numel() == c:
+            b_into = ctx.bias_obj.grad
         if ctx.act != ACT_NONE:
-            g, gb_fused = _MaskMul.apply(gy, y, ctx.act, c, want_b)      # activation backward + bias column sums: one pass
+            g, gb_fused = _MaskMul.apply(gy, y, ctx.act, c, want_b, b_into)      # activation backward + bias column sums: one pass
         else:
             g = gy
         gx = _Tr.apply(op, g, w) if ctx.needs_input_grad[1] else None
@@ -371,7 +384,12 @@ class _Fwd(Function):
         gb = None
         if want_b:
             # the bias gradient is never differentiated again on this path (the GP contributes exactly zero to biases)
-            gb = gb_fused if gb_fused is not None else _bias_grad(g.detach(), c)
+            if gb_fused is not None:
+                gb = None if b_into is not None else gb_fused
+            elif b_into is not None:
+                _bias_grad(g.detach(), c, into=b_into)
+            else:
+                gb = _bias_grad(g.detach(), c)
         return None, gx, gw, gb, None
 
 

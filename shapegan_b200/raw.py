@@ -176,8 +176,34 @@ def _call(name, *args):
     L.check(getattr(L.lib(), name)(*args, stream()), name)
 
 
+class _SumArena:
+    """Zero-initialised double workspaces for the column-reducing kernels, cut from one memset'ed arena instead of one
+    `torch.zeros` (= one fill launch) per reduction.  Every slice is handed out once.  An arena created while a CUDA graph
+    is being captured belongs to that graph (its memset is a node of the graph and re-runs on every replay); it is never
+    shared with work outside the capture, and vice versa."""
+    SIZE = 1 << 15
+
+    def __init__(self):
+        self.buf, self.off, self.captured, self.device = None, 0, False, None
+
+    def take(self, n, device):
+        n_al = (n + 7) & ~7
+        if n_al > self.SIZE:
+            return torch.zeros(n, dtype=torch.float64, device=device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.buf is None or self.device != device or self.off + n_al > self.SIZE or self.captured != capturing:
+            self.buf = torch.zeros(self.SIZE, dtype=torch.float64, device=device)
+            self.off, self.captured, self.device = 0, capturing, device
+        out = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return out
+
+
+_SUMS = _SumArena()
+
+
 def dsums(n, device):
-    return torch.zeros(n, dtype=torch.float64, device=device)
+    return _SUMS.take(n, device)
 
 
 def act_bwd(ga, y, act, c, want_sums=False, want_g=True):
