@@ -47,6 +47,9 @@ struct IgemmP {
   int use_tma, bx, by, bz, bnn, gx, gy, gz;
   CUtensorMap tmA[2];    // per plane
   CUtensorMap tmA2[2];   // second DENSE source
+  // halo variant (sg_igemm_halo_kernel): one strided box of (8+1) x 8 x (2 mt + 1) grid points serves the 4 taps (qz, qx)
+  int halo; unsigned blk_bytes; int b_stages;
+  CUtensorMap tmH;
 };
 
 struct SmemHeader {
@@ -57,6 +60,8 @@ struct SmemHeader {
   uint32_t tmem_base;
   uint32_t pad_[3];
   float sbias[256];      // bias of the current N tile (epilogue broadcast reads)
+  uint64_t blk_full[2];  // halo kernel: A blocks
+  uint64_t blk_empty[2];
 };
 
 template <class P>
@@ -603,6 +608,174 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ================================================================================================ halo-reuse variant
+// Conv3d k4 s2 p1 forward gather (SG_MODE_CONV) and ConvTranspose3d k4 s2 p1 per-class gather (SG_MODE_CONVT) on an 8 x 8 x gz
+// row grid, bf16 (planes = 1), C % 64 == 0.  The plain kernel loads one 128-row A tile per (tap, 64-channel chunk): the TMA unit
+// needs ~3.5 clk per gathered 128-byte row, which bounds those layers.  Here the taps that differ only by +1 in
+// x and/or z of the stride-2 (or unit-stride) sample grid -- (qz, qx) in {0,1}^2 for a fixed (kh | th, parity pz, px) -- read ONE
+// halo block [(2 mt + 1) z][8 y][9 x] rows of 128 B: tap (qz, qx) is the block viewed from row (qz*8*9 + qx) on, 8-row groups
+// 9 rows apart.  tcgen05 applies the 128B swizzle to absolute shared-memory address bits (tools/exp_umma_view.cu), so such
+// shifted, non-1024-aligned views with SBO = 9*128 are valid A operands.  2.4x (mt = 1) to 2.8x (mt = 2) fewer TMA rows.
+//   smem: [header][2 A blocks][b_stages weight tiles]; roles as in sg_igemm_kernel; ksplit = 1.
+struct HaloSeq {     // position in the K sequence: group (kh|th, pz, px) -> channel chunk -> 4 taps
+  int grp, cc, t4;
+};
+
+__device__ __forceinline__ int halo_tap(const IgemmP& p, int grp, int t4) {
+  const int qz = t4 >> 1, qx = t4 & 1;
+  if (p.mode == SG_MODE_CONV) {          // grp = kh*4 + pz*2 + px ; k = 2 q + parity
+    const int kh = grp >> 2, pz = (grp >> 1) & 1, px = grp & 1;
+    return (2 * qz + pz) * 16 + kh * 4 + (2 * qx + px);
+  }
+  const int th = grp;                      // CONVT: shift q = 1 - t  (offset = (parity ? 0 : -1) + q)
+  return (1 - qz) * 4 + th * 2 + (1 - qx);
+}
+
+__global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const __grid_constant__ IgemmP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+  uint8_t* blk0 = smem + kSmemHeader;
+  uint8_t* bst0 = blk0 + 2 * (size_t)p.blk_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int SB = p.b_stages;
+  const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+  const int cchunks = p.aC >> 6;
+  const int ngroups = (p.mode == SG_MODE_CONV) ? 16 : 2;
+  if (tid == 0) {
+    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], kBLoaderThreads); mbar_init(&hdr->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128);
+      mbar_init(&hdr->blk_full[i], 1); mbar_init(&hdr->blk_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(&hdr->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0) atomicExch(p.err, kErrSmemAlign);
+    __trap();
+  }
+
+  if (warp == 0) {
+    // ================================================================ TMA producer: one halo block per (group, channel chunk)
+    if (elect_one()) {
+      tma_prefetch_desc(&p.tmH);
+      int bi = 0; uint32_t bph = 0;
+      const int lgz = 31 - __clz(max(p.gz, 1));
+      for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+        int cls, nt, mtile, ks;
+        decode_work(p, w, cls, nt, mtile, ks);
+        const int pd = (cls >> 2) & 1, phh = (cls >> 1) & 1, pw = cls & 1;
+        const uint32_t row0 = (uint32_t)(mtile * p.mt) * kTileRows;        // rows = ((n*gz + z)*8 + y)*8 + x
+        const int z0 = (int)((row0 >> 6) & (uint32_t)(p.gz - 1)), n0 = (int)(row0 >> (6 + lgz));
+        for (int grp = 0; grp < ngroups; ++grp) {
+          int x, y, z;
+          if (p.mode == SG_MODE_CONV) {
+            const int kh = grp >> 2, pz = (grp >> 1) & 1, px = grp & 1;
+            x = -1 + px; y = -1 + kh; z = 2 * z0 - 1 + pz;
+          } else {
+            const int th = grp;
+            x = pw ? 0 : -1; y = phh ? 1 - th : -th; z = z0 + (pd ? 0 : -1);
+          }
+          for (int cc = 0; cc < cchunks; ++cc) {
+            mbar_wait(&hdr->blk_empty[bi], bph ^ 1, p.err);
+            mbar_arrive_expect_tx(&hdr->blk_full[bi], p.blk_bytes);
+            tma_load_5d(smem_u32(blk0 + (size_t)bi * p.blk_bytes), &p.tmH, cc * 64, x, y, z, n0, &hdr->blk_full[bi]);
+            if (++bi == 2) { bi = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================================================ weight-tile loaders (warps 1-3, cp.async), K sequence order
+    const int bt = tid - 32;
+    int s = 0; uint32_t ph = 0;
+    int pending = 0, oldest = 0;
+    const uint32_t pieces = (uint32_t)p.bn * 8u;
+    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+      int cls, nt, mtile, ks;
+      decode_work(p, w, cls, nt, mtile, ks);
+      const char* bcls = p.b + ((size_t)cls * p.kchunks * p.n_pad + (size_t)nt * p.bn) * 128;
+      for (int grp = 0; grp < ngroups; ++grp)
+        for (int cc = 0; cc < cchunks; ++cc)
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int kc = halo_tap(p, grp, t4) * cchunks + cc;
+            const char* bsrc = bcls + (size_t)kc * p.n_pad * 128;
+            mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+            const uint32_t b_dst = smem_u32(bst0 + (size_t)s * b_tile_bytes);
+            for (uint32_t i = (uint32_t)bt; i < pieces; i += kBLoaderThreads) cp_async16(b_dst + i * 16u, bsrc + (size_t)i * 16u, 16u);
+            cp_async_commit();
+            if (++pending > 1) {
+              cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+              if (++oldest == SB) oldest = 0;
+              --pending;
+            }
+            if (++s == SB) { s = 0; ph ^= 1; }
+          }
+    }
+    while (pending > 0) {
+      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+      if (++oldest == SB) oldest = 0;
+      --pending;
+    }
+  } else if (warp == 4) {
+    // ================================================================ MMA issuer (one elected thread)
+    const uint32_t idesc = umma_idesc(128, p.bn, false, false);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    int bi = 0; uint32_t bph = 0;
+    if (elect_one())
+    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
+      const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
+      const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
+      mbar_wait(&hdr->accempty[ab], aph ^ 1, p.err);
+      tc_fence_after();
+      bool first = true;
+      for (int grp = 0; grp < ngroups; ++grp)
+        for (int cc = 0; cc < cchunks; ++cc) {
+          mbar_wait(&hdr->blk_full[bi], bph, p.err);
+          const uint32_t blk = smem_u32(blk0 + (size_t)bi * p.blk_bytes);
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int qz = t4 >> 1, qx = t4 & 1;
+            mbar_wait(&hdr->full[s], ph, p.err);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(bst0 + (size_t)s * b_tile_bytes);
+            for (int sub = 0; sub < p.mt; ++sub) {
+              const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
+              const uint32_t a_view = blk + (uint32_t)(((sub * 2 + qz) * 8) * 9 + qx) * 128u;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t da = umma_desc(a_view + kk * 32, 16, 9 * 128);
+                const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
+                umma_bf16(d_addr, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+              }
+            }
+            first = false;
+            umma_commit(&hdr->empty[s]);
+            if (++s == SB) { s = 0; ph ^= 1; }
+          }
+          umma_commit(&hdr->blk_empty[bi]);
+          if (++bi == 2) { bi = 0; bph ^= 1; }
+        }
+      umma_commit(&hdr->accfull[ab]);
+    }
+    __syncwarp();
+  } else {
+    switch (p.act) {
+      case ACT_NONE: epilogue_role<ACT_NONE>(p, hdr, tmem_base, p.kchunks); break;
+      case ACT_LRELU: epilogue_role<ACT_LRELU>(p, hdr, tmem_base, p.kchunks); break;
+      case ACT_RELU: epilogue_role<ACT_RELU>(p, hdr, tmem_base, p.kchunks); break;
+      default: epilogue_role<-1>(p, hdr, tmem_base, p.kchunks); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ================================================================================================ host launcher
 static int igemm_validate(const sg_igemm_args* a) {
   if (!a) return sg_fail(-1, "sg_igemm: null args");
@@ -744,6 +917,42 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
       p.use_tma = ok ? 1 : 0;
     }
   }
+  { const char* dg = getenv("SG_B200_IGEMM_DIAG"); p.diag = dg ? atoi(dg) : 0; }
+  // ---- halo-reuse variant (see sg_igemm_halo_kernel): 8 x 8 x gz row grids, bf16
+  {
+    const bool conv = a->mode == SG_MODE_CONV;
+    const char* no_halo = getenv("SG_B200_NO_HALO");
+    if (p.use_tma && !(no_halo && no_halo[0] == '1') && a->planes == 1 && (conv || a->mode == SG_MODE_CONVT) && p.gx == 8 && p.gy == 8 &&
+        p.bx == 8 && p.by == 8 && is_pow2(p.gz) && p.gz % (2 * mt) == 0 && ksplit == 1 && (a->a.c % 64) == 0 && !p.diag) {
+      const uint64_t C = (uint64_t)a->a.c, W = (uint64_t)a->a.w, H = (uint64_t)a->a.h, D = (uint64_t)a->a.d;
+      uint64_t dims[5] = {C, W, H, D, (uint64_t)a->a.n};
+      uint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, D * H * W * C * 2};
+      const uint32_t m = conv ? 2u : 1u;
+      const uint32_t zp = (uint32_t)(2 * mt + 1);
+      uint32_t box[5] = {64, m * 9, m * 8, m * zp, 1};
+      uint32_t es[5] = {1, m, m, m, 1};
+      p.blk_bytes = 9u * 8u * zp * 128u;
+      const unsigned b_tile = (unsigned)bn * 128u;
+      const long long room = 227LL * 1024 - kSmemHeader - 2LL * p.blk_bytes;
+      p.b_stages = (int)std::min<long long>(kMaxStages, room / b_tile);
+      if (p.b_stages >= 3 && tma_make_map(&p.tmH, a->a.ptr, 5, dims, str, box, es)) p.halo = 1;
+    }
+  }
+  if (p.halo) {
+    const size_t hsmem = kSmemHeader + 2 * (size_t)p.blk_bytes + (size_t)p.b_stages * (size_t)bn * 128;
+    static bool hattr_set = false;
+    if (!hattr_set) {
+      cudaError_t e = cudaFuncSetAttribute(sg_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+      hattr_set = true;
+    }
+    const int hgrid = (int)std::min<long long>(p.work_total, sms);
+    sg_igemm_halo_kernel<<<hgrid, kIgemmThreads, hsmem, (cudaStream_t)stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+    sg_count_launch();
+    return 0;
+  }
   const size_t smem = kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
@@ -751,7 +960,6 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
-  { const char* dg = getenv("SG_B200_IGEMM_DIAG"); p.diag = dg ? atoi(dg) : 0; }
   int grid = (int)std::min<long long>(p.work_total, sms);
   { const char* gg = getenv("SG_B200_IGEMM_GRID"); if (gg && atoi(gg) > 0) grid = std::min(grid, atoi(gg)); }   // measurement only
   sg_igemm_kernel<<<grid, kIgemmThreads, smem, (cudaStream_t)stream>>>(p);

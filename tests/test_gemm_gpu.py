@@ -129,6 +129,40 @@ def test_convt_fwd(planes, b, r, cin, cout):
     check_error_word()
 
 
+@pytest.mark.parametrize('mt', [1, 2])
+@pytest.mark.parametrize('mode,b,cin,cout', [('conv', 2, 64, 128), ('conv', 3, 128, 64), ('convt', 2, 64, 64), ('convt', 3, 128, 32)])
+def test_halo_variant(mode, b, cin, cout, mt, monkeypatch):
+    """8 x 8 x 8 row grids, bf16, C % 64 == 0: the halo-reuse kernel (one strided TMA block serves the four taps that differ by +1
+    in x / z; shifted, non-1024-aligned UMMA operand views) against torch, and against the plain one-tile-per-tap kernel."""
+    L, raw = _imports()
+    bias = rnd((cout,), 3)
+    outs = []
+    for no_halo in ('0', '1'):
+        monkeypatch.setenv('SG_B200_NO_HALO', no_halo)
+        if mode == 'conv':
+            r = 16
+            x = rnd((b, r, r, r, cin), 1)
+            w = rnd((cout, cin, 4, 4, 4), 2, 0.05)
+            rows = b * 8 ** 3
+            out = torch.empty((rows, cout), dtype=torch.float32, device='cuda')
+            raw.igemm(L.MODE_CONV, 1, raw.to_planes(x, 1), (b, r, r, r, cin), rows, 64 * cin, raw.pack_conv_fwd(w, 1), cout, out, cout,
+                      out_kind=L.OUT_F32, bias=bias, mt=mt)
+            ref = F.conv3d(q(x, 1).permute(0, 4, 1, 2, 3), q(w, 1), bias.double(), stride=2, padding=1).permute(0, 2, 3, 4, 1).reshape(rows, cout)
+        else:
+            r = 8
+            x = rnd((b, r, r, r, cin), 1)
+            w = rnd((cin, cout, 4, 4, 4), 2, 0.05)
+            out = torch.zeros((b * 16 ** 3, cout), dtype=torch.float32, device='cuda')
+            raw.igemm(L.MODE_CONVT, 1, raw.to_planes(x, 1), (b, r, r, r, cin), b * r ** 3, 8 * cin, raw.pack_convt_fwd(w, 1), cout, out, cout,
+                      out_kind=L.OUT_F32, bias=bias, out_dims=(16, 16, 16), mt=mt)
+            ref = F.conv_transpose3d(q(x, 1).permute(0, 4, 1, 2, 3), q(w, 1), bias.double(), stride=2, padding=1)
+            ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, cout)
+        report('halo=%s %s mt%d %s' % ('off' if no_halo == '1' else 'on', mode, mt, (b, cin, cout)), out, ref, TOL_F32)
+        outs.append(out.clone())
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-3 * max(1.0, outs[1].abs().max().item())
+    check_error_word()
+
+
 @pytest.mark.parametrize('planes', [1, 2])
 def test_conv_dgrad_and_convt_dgrad(planes):
     L, raw = _imports()
