@@ -227,7 +227,7 @@ def cpu_baseline(workload):
 
 # --------------------------------------------------------------------------------------------------------- roofline probe
 def roofline_probe(flush):
-    """Time the dominant kernel alone: sg_igemm (MODE_CONV) for Conv3d(64->128) at B=64, bf16."""
+    """Time the dominant kernel alone: sg_igemm (MODE_CONV, halo-reuse variant) for Conv3d(64->128) at B=64, bf16."""
     from shapegan_b200 import _lib as L
     from shapegan_b200 import raw
     b, r, cin, cout = 64, 16, 64, 128
@@ -254,12 +254,12 @@ def roofline_probe(flush):
     pk, src = peaks()
     achieved = FLOPS_D2_FWD / (avg * 1e-3) / 1e12
     return {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops'],
-            'traffic': 34.72e6, 'traffic_source': 'dram__bytes_read+write per launch, ncu --set full (profiles/r01g_ncu_prof_conv.txt); '
+            'traffic': 34.69e6, 'traffic_source': 'dram__bytes_read+write per launch, ncu --set full (profiles/r01h_ncu_prof_conv.txt); '
             'algorithmic DRAM bytes 33.6 MB input + 1.0 MB weights (the 8.4 MB output stays in L2)',
-            'kernel': 'sg_igemm_kernel MODE_CONV Conv3d(64->128,k4,s2,p1) fwd B=64 (34.36 GFLOP/launch)',
+            'kernel': 'sg_igemm_halo_kernel MODE_CONV Conv3d(64->128,k4,s2,p1) fwd B=64 (34.36 GFLOP/launch)',
             'launch_ms': avg, 'peak_source': src + ', burst (kernel timed alone)',
-            'note': 'measured per-SM ceilings for this tile shape (tools/diag_conv.py, DESIGN.md 4): TMA ingest ~47 B/clk/SM, '
-                    'SS-mode 128x128x16 MMA ~108 clk (operand reads out of shared memory), i.e. shared-memory bandwidth, not L2 or HBM'}
+            'note': 'halo-reuse variant (one strided TMA block serves 4 taps); measured per-SM ceilings of the plain one-tile-per-tap kernel '
+                    '(tools/diag_conv.py, DESIGN.md 4): ~3.5 clk per gathered 128-byte TMA row, SS-mode 128x128x16 MMA ~108 clk'}
 
 
 def sdfnet_probe(dev, world):
