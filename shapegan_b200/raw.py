@@ -190,7 +190,7 @@ class _SumArena:
         n_al = (n + 7) & ~7
         if n_al > self.SIZE:
             return torch.zeros(n, dtype=torch.float64, device=device)
-        capturing = torch.cuda.is_current_stream_capturing()
+        capturing = torch.device(device).type == 'cuda' and torch.cuda.is_current_stream_capturing()
         if self.buf is None or self.device != device or self.off + n_al > self.SIZE or self.captured != capturing:
             self.buf = torch.zeros(self.SIZE, dtype=torch.float64, device=device)
             self.off, self.captured, self.device = 0, capturing, device

@@ -130,3 +130,24 @@ print(' '.join(out))
         assert r.returncode == 0, r.stderr[-2000:]
         res[tag] = r.stdout.strip().split()
     assert res['ref'] == res['ours']
+
+
+def test_sum_arena_slices_are_zeroed_disjoint_and_refreshed():
+    """raw.dsums(): reductions take their double workspaces from one memset'ed arena; every slice is handed out once."""
+    from shapegan_b200 import raw
+    dev = torch.device('cpu')
+    arena = raw._SumArena()
+    a = arena.take(300, dev)
+    b = arena.take(5, dev)
+    assert a.dtype == torch.float64 and a.numel() == 300 and b.numel() == 5
+    assert a.abs().sum().item() == 0 and b.abs().sum().item() == 0
+    a += 1.0
+    assert b.abs().sum().item() == 0                                # disjoint
+    assert b.data_ptr() - a.data_ptr() == 304 * 8                   # 8-element granularity inside one buffer
+    first = arena.buf
+    for _ in range(arena.SIZE // 304 + 2):
+        c = arena.take(300, dev)
+        assert c.abs().sum().item() == 0
+    assert arena.buf is not first                                   # exhausted arena replaced by a fresh zeroed one
+    big = arena.take(arena.SIZE + 1, dev)
+    assert big.numel() == arena.SIZE + 1 and big.abs().sum().item() == 0
