@@ -224,6 +224,9 @@ const char* sg_last_error(void);
 int sg_device_error_word(int32_t** dev_ptr); /* device word set by a kernel watchdog (mbarrier timeout) */
 int sg_check_device_error(void);               /* diagnostic, synchronises: returns and clears that word */
 int sg_num_sms(void);
+/* 0 when `stream` is not being captured into a CUDA graph, else the unique id of that capture (host-side weight-image
+ * caches must not reuse an image packed OUTSIDE the capture: the graph would replay with frozen weights) */
+int sg_stream_capture_id(void* stream, unsigned long long* id_out);
 long long sg_launch_count(void);               /* kernels launched by this library since load (bench gpu_launches) */
 /* diagnostics (tools/diag_conv.py): clock64 trace [3][1024] {producer got a stage, MMA warp got its data, MMAs issued} of CTA 0
  * of the last sg_igemm launched with env SG_B200_IGEMM_DIAG & 128; synchronises */

@@ -62,6 +62,7 @@ SYMBOLS = {
     'sg_check_device_error': (c_int32, []),
     'sg_num_sms': (c_int32, []),
     'sg_launch_count': (c_longlong, []),
+    'sg_stream_capture_id': (c_int32, [c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]),
     'sg_debug_igemm_trace': (c_int32, [ctypes.POINTER(c_longlong), c_int32]),
     'sg_igemm': (c_int32, [ctypes.POINTER(SgIgemmArgs), c_void_p]),
     'sg_wgrad_plan': (c_int32, [ctypes.POINTER(SgWgradArgs), ctypes.POINTER(c_size_t)]),

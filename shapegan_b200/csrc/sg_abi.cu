@@ -96,6 +96,18 @@ extern "C" int sg_num_sms(void) {
   return sms;
 }
 
+// 0 when `stream` is not being captured into a CUDA graph, else the capture sequence's unique id: lets host-side caches tell
+// "packed in THIS capture" (its pack kernel is a node of the graph and re-runs on every replay) from "packed earlier".
+extern "C" int sg_stream_capture_id(void* stream, unsigned long long* id_out) {
+  if (!id_out) return sg_fail(-1, "sg_stream_capture_id: null");
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  cudaError_t e = cudaStreamGetCaptureInfo((cudaStream_t)stream, &st, &id);
+  if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+  *id_out = (st == cudaStreamCaptureStatusActive) ? id : 0ull;
+  return 0;
+}
+
 extern "C" int sg_device_error_word(int32_t** dev_ptr) {
   int* p = sg_error_word();
   if (!p) return sg_fail(-1, "sg_device_error_word: no device symbol (is a CUDA device present?)");

@@ -5,6 +5,8 @@ Extension (kept out of the reference signature's way): `forward(points, latent_c
 `shape_index` (int [N]) is given, `latent_codes` is a [S, L] table and row i uses `latent_codes[shape_index[i]]`.
 This is what the reference's callers compute with `latent_codes[model_indices, :]` (train_sdf_autodecoder.py:80) or
 `.repeat(...)` (sdf_net.py:64, train_hybrid_progressive_gan.py:92) without materialising the [N, L] copy."""
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -82,9 +84,22 @@ class SDFNet(SavableModule):
         n = points.shape[0]
         if n == 0:
             return torch.zeros((0,), dtype=torch.float32, device=points.device)
+        # the kernels take raw pointers: shape errors the reference would get from torch.cat (model/sdf_net.py:57) are raised here
+        if points.dim() != 2 or points.shape[1] != 3:
+            raise RuntimeError('SDFNet.forward: points must be [N, 3], got %s' % (tuple(points.shape),))
+        if latent_codes.dim() != 2 or latent_codes.shape[1] != self.latent_code_size:
+            raise RuntimeError('SDFNet.forward: latent_codes must be [*, %d], got %s' % (self.latent_code_size, tuple(latent_codes.shape)))
         idx = None
         if shape_index is not None:
+            if shape_index.numel() != n:
+                raise RuntimeError('SDFNet.forward: shape_index has %d entries for %d points' % (shape_index.numel(), n))
             idx = shape_index.to(device=points.device, dtype=torch.int32).contiguous()
+            if os.environ.get('SG_B200_CHECK_INDEX') == '1' and n > 0:      # debug only: synchronises
+                lo, hi = int(idx.min()), int(idx.max())
+                if lo < 0 or hi >= latent_codes.shape[0]:
+                    raise RuntimeError('SDFNet.forward: shape_index out of range [0, %d)' % latent_codes.shape[0])
+        elif latent_codes.shape[0] != n:
+            raise RuntimeError('SDFNet.forward: %d latent rows for %d points (sizes must match, model/sdf_net.py:57)' % (latent_codes.shape[0], n))
         out = sdfnet_apply(points.float(), latent_codes.float(), idx, self._params())
         return out.squeeze()
 

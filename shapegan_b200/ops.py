@@ -30,8 +30,11 @@ r64 = lambda v: raw.round_up(v, 64)   # noqa: E731
 class _PackCache:
     """fp32 parameter -> tensor-core operand image, cached per parameter OBJECT (a uid stamped on the tensor; a
     device address can be recycled by the caching allocator, so it is not an identity) and validated by
-    (`_version`, data_ptr, shape).  An optimizer step or load_state_dict bumps `_version`; `.data` mutations do not:
-    call invalidate() (our clip_weights does).  Entries die with their parameter (weakref.finalize)."""
+    (`_version`, data_ptr, shape) AND the CUDA-graph capture the image was packed in (0 = eager).  An optimizer step or
+    load_state_dict bumps `_version`; `.data` mutations do not: call invalidate() (our clip_weights does).
+    An image packed outside a capture is never reused inside one (and vice versa): the pack kernel has to be a node of
+    the graph, or every replay would run on the weights of capture time while the optimizer keeps updating the real ones.
+    Entries die with their parameter (weakref.finalize)."""
 
     def __init__(self):
         self.store = {}
@@ -53,16 +56,26 @@ class _PackCache:
         for key in [k for k in self.store if k[0] == uid]:
             self.store.pop(key, None)
 
+    def lookup(self, key, sig):
+        """cached payload for `key` if it was built from `sig` in the current capture context, else None"""
+        hit = self.store.get(key)
+        if hit is not None and hit[0] == sig and hit[2] == raw.capture_id():
+            return hit[1]
+        return None
+
+    def put(self, key, sig, payload):
+        self.store[key] = (sig, payload, raw.capture_id())
+
     def get(self, w, kind, planes, fn):
         uid = self._uid(w)
+        if uid is None:
+            return fn(w.detach(), planes)
         key = (uid, kind, planes)
         sig = (w._version, w.data_ptr(), tuple(w.shape))
-        hit = self.store.get(key) if uid is not None else None
-        if hit is not None and hit[0] == sig:
-            return hit[1]
-        img = fn(w.detach(), planes)
-        if uid is not None and not torch.cuda.is_current_stream_capturing():
-            self.store[key] = (sig, img)
+        img = self.lookup(key, sig)
+        if img is None:
+            img = fn(w.detach(), planes)
+            self.put(key, sig, img)
         return img
 
     def invalidate(self):
@@ -78,6 +91,35 @@ def invalidate_weight_cache():
 
 def _planes():
     return config.planes()
+
+
+# First-order backward passes of the Step classes (train.py) let the layer Functions accumulate weight / bias gradients
+# straight into the allocated `.grad` views of the flat gradient arena (what AccumulateGrad would do with a returned tensor,
+# minus the temporary and the add kernel).  Opt-in: `torch.autograd.grad(out, x)` or `backward(inputs=[x])` through a layer
+# must NOT touch parameter gradients, and ctx.needs_input_grad cannot tell those calls from a plain `.backward()`.
+_ARENA_ACCUMULATE = [False]
+
+
+class arena_backward:
+    """with ops.arena_backward(): loss.backward()   -- parameter gradients accumulate in place into their `.grad`"""
+
+    def __enter__(self):
+        self.prev = _ARENA_ACCUMULATE[0]
+        _ARENA_ACCUMULATE[0] = True
+
+    def __exit__(self, *exc):
+        _ARENA_ACCUMULATE[0] = self.prev
+        return False
+
+
+def _into_grad(p, numel=None):
+    """the parameter's allocated .grad if in-place accumulation is active and legal for this backward, else None"""
+    if not _ARENA_ACCUMULATE[0] or torch.is_grad_enabled():
+        return None
+    g = p.grad
+    if g is None or not g.is_contiguous() or (numel is not None and g.numel() != numel):
+        return None
+    return g
 
 
 def _new(shape, device):
@@ -364,10 +406,7 @@ class _Fwd(Function):
         gb_fused = None
         # first-order backward with an allocated bias .grad (flat gradient arena): the bias sums accumulate in place, like the
         # weight gradient below -- no temporary, no AccumulateGrad add kernel
-        b_into = None
-        if want_b and (not torch.is_grad_enabled()) and ctx.bias_obj.grad is not None and ctx.bias_obj.grad.is_contiguous() \
-                and ctx.bias_obj.grad.numel() == c:
-            b_into = ctx.bias_obj.grad
+        b_into = _into_grad(ctx.bias_obj, c) if want_b else None
         if ctx.act != ACT_NONE:
             g, gb_fused = _MaskMul.apply(gy, y, ctx.act, c, want_b, b_into)      # activation backward + bias column sums: one pass
         else:
@@ -375,10 +414,11 @@ class _Fwd(Function):
         gx = _Tr.apply(op, g, w) if ctx.needs_input_grad[1] else None
         gw = None
         if ctx.needs_input_grad[2]:
-            if (not torch.is_grad_enabled()) and w.grad is not None and w.grad.is_contiguous() and hasattr(op, 'wgrad_into'):
-                # first-order backward with an allocated .grad (e.g. the flat gradient arena): accumulate in place, exactly
-                # what AccumulateGrad would do with the returned tensor, minus the temporary and the extra add kernel
-                op.wgrad_into(x, g, w.grad)
+            w_into = _into_grad(w) if hasattr(op, 'wgrad_into') else None
+            if w_into is not None:
+                # first-order backward of a Step class with an allocated .grad (the flat gradient arena): accumulate in place,
+                # exactly what AccumulateGrad would do with the returned tensor, minus the temporary and the extra add kernel
+                op.wgrad_into(x, g, w_into)
             else:
                 gw = _Wgrad.apply(op, x, g, w)
         gb = None

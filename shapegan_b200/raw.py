@@ -11,6 +11,15 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def capture_id():
+    """0 outside CUDA-graph capture, else the unique id of the capture running on the current stream"""
+    if not torch.cuda.is_current_stream_capturing():
+        return 0
+    cid = ctypes.c_ulonglong(0)
+    L.check(L.lib().sg_stream_capture_id(stream(), ctypes.byref(cid)), 'sg_stream_capture_id')
+    return int(cid.value)
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -180,17 +189,17 @@ class _SumArena:
     """Zero-initialised double workspaces for the column-reducing kernels, cut from one memset'ed arena instead of one
     `torch.zeros` (= one fill launch) per reduction.  Every slice is handed out once.  An arena created while a CUDA graph
     is being captured belongs to that graph (its memset is a node of the graph and re-runs on every replay); it is never
-    shared with work outside the capture, and vice versa."""
+    shared with work outside the capture or with another capture."""
     SIZE = 1 << 15
 
     def __init__(self):
-        self.buf, self.off, self.captured, self.device = None, 0, False, None
+        self.buf, self.off, self.captured, self.device = None, 0, 0, None
 
     def take(self, n, device):
         n_al = (n + 7) & ~7
         if n_al > self.SIZE:
             return torch.zeros(n, dtype=torch.float64, device=device)
-        capturing = torch.device(device).type == 'cuda' and torch.cuda.is_current_stream_capturing()
+        capturing = capture_id() if torch.device(device).type == 'cuda' else 0      # the capture's id, 0 = eager
         if self.buf is None or self.device != device or self.off + n_al > self.SIZE or self.captured != capturing:
             self.buf = torch.zeros(self.SIZE, dtype=torch.float64, device=device)
             self.off, self.captured, self.device = 0, capturing, device

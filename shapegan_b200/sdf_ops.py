@@ -27,9 +27,6 @@ def _pack_lin_t(w, planes, n_valid, n_pad, col0=0):
     return raw.pack_b(view, planes, n_valid, r64(out_f), 1, r64(out_f), out_f, s_n0=1, s_tap=0, s_c=w.stride(0), n_pad=n_pad)
 
 
-_FUSED_CACHE = {}
-
-
 def fused_enabled():
     import os
     return os.environ.get('SG_B200_NO_FUSED_SDF') != '1'
@@ -37,11 +34,11 @@ def fused_enabled():
 
 def _fused_pack(w, b):
     """28 weight chunks (stream order of sg_sdfnet.cu) + fp32 aux block; cached on the parameter versions."""
-    uid = PACK_CACHE._uid(w[0])
+    key = (PACK_CACHE._uid(w[0]), 'sdf_fused_fwd', 1)
     sig = tuple((t._version, t.data_ptr()) for t in list(w) + list(b))
-    hit = _FUSED_CACHE.get(uid)
-    if hit is not None and hit[0] == sig:
-        return hit[1], hit[2]
+    hit = PACK_CACHE.lookup(key, sig)
+    if hit is not None:
+        return hit
     dev = w[0].device
     chunk = 32768
     img = torch.empty(28 * chunk, dtype=torch.uint8, device=dev)
@@ -66,8 +63,7 @@ def _fused_pack(w, b):
     xb5 = torch.cat((w5[:, 256:259], b[4].detach().unsqueeze(1)), 1).reshape(128, 2, 4).permute(0, 2, 1)
     aux = torch.cat([xb1.reshape(-1), xb5.reshape(-1)] + [b[i].detach() for i in (1, 2, 3, 5, 6)] +
                     [w[7].detach().reshape(-1), b[7].detach().reshape(-1)]).contiguous().float()
-    if not torch.cuda.is_current_stream_capturing():
-        _FUSED_CACHE[uid] = (sig, img, aux)
+    PACK_CACHE.put(key, sig, (img, aux))
     return img, aux
 
 
@@ -218,20 +214,19 @@ def fused_bwd_enabled():
 
 def _fused_pack_t(w):
     """24 transposed weight chunks in the stream order of sg_sdfnet_bwd_kernel: layers2.4, 2.2, 2.0[:, :256], layers1.6, 1.4, 1.2."""
-    uid = PACK_CACHE._uid(w[1])
+    key = (PACK_CACHE._uid(w[1]), 'sdf_fused_bwd', 1)
     order = (6, 5, 4, 3, 2, 1)
     sig = tuple((w[i]._version, w[i].data_ptr()) for i in order)
-    hit = _FUSED_CACHE.get(('t', uid))
-    if hit is not None and hit[0] == sig:
-        return hit[1]
+    hit = PACK_CACHE.lookup(key, sig)
+    if hit is not None:
+        return hit
     chunk = 32768
     img = torch.empty(24 * chunk, dtype=torch.uint8, device=w[1].device)
     for j, i in enumerate(order):
         t = w[i].detach()
         # B[n = in-feature][k = out-feature] = W[k, n]  (first 256 in-features: layers2.0 keeps its xyz/latent columns out)
         raw.pack_b(t, 1, HID, HID, 1, HID, HID, s_n0=1, s_tap=0, s_c=t.stride(0), n_pad=HID, out=img[j * 4 * chunk:(j + 1) * 4 * chunk])
-    if not torch.cuda.is_current_stream_capturing():
-        _FUSED_CACHE[('t', uid)] = (sig, img)
+    PACK_CACHE.put(key, sig, img)
     return img
 
 

@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import raw
+from .ops import arena_backward
 
 
 class FlatOptimizer:
@@ -107,7 +108,8 @@ class WGANStep:
         closs = torch.mean(score[:b]) - torch.mean(score[b:])
         if self.gp:
             closs = closs + gradient_penalty(cri, real, fake.squeeze(1), alpha, self.gp_weight)
-        closs.backward()                                               # :69
+        with arena_backward():                                               # :69
+            closs.backward()
         self.copt.step()                                               # :70-71 (clip fused)
         self.gopt.zero_grad(); self.copt.zero_grad()                    # :75-76
         # The reference's backward here also fills the critic's weight gradients, which :62-63 of the next batch zeroes
@@ -116,7 +118,8 @@ class WGANStep:
             q.requires_grad_(False)
         try:
             gloss = -torch.mean(cri(gen(z_gen)))                       # :78-82
-            gloss.backward()                                           # :83
+            with arena_backward():                                           # :83
+                gloss.backward()
         finally:
             for q in self.copt.params:
                 q.requires_grad_(True)
@@ -138,18 +141,21 @@ class GANStep:
         b = real.shape[0]
         self.gopt.zero_grad(); self.dopt.zero_grad()
         gloss = -torch.mean(torch.log(dis(gen(z_gen))))                # :61-65
-        gloss.backward()
+        with arena_backward():
+            gloss.backward()
         self.gopt.step()
         self.dopt.zero_grad()
         with torch.no_grad():
             fake = gen(z_dis)
         out_fake = dis(fake)
         floss = bce(out_fake, torch.zeros(b, device=real.device))      # :76-79
-        floss.backward()
+        with arena_backward():
+            floss.backward()
         self.dopt.step()
         self.dopt.zero_grad()
         vloss = bce(dis(real), torch.ones(b, device=real.device))      # :82-85
-        vloss.backward()
+        with arena_backward():
+            vloss.backward()
         self.dopt.step()
         return gloss.detach(), floss.detach(), vloss.detach()
 
@@ -162,21 +168,20 @@ class AutodecoderStep:
         self.table = latent_table.detach().clone().requires_grad_(True)
         self.nopt = FlatOptimizer(sdf_net.parameters(), 'adam', lr, world_size=world_size)
         self.lopt = FlatOptimizer([self.table], 'adam', lr, world_size=world_size)
-        self._counts_key, self._counts = None, None
 
     def __call__(self, points, sdf, shape_index):
         """points [N,3], sdf [N], shape_index int32 [N] (= point_index // POINTCLOUD_SIZE, :78 with the D6 fix)."""
         self.nopt.zero_grad(); self.lopt.zero_grad()                    # :84-86
         out = self.net(points, self.table, shape_index)                # :80,87 without materialising table[index]
-        # mean(z_batch^2) over the gathered rows == sum_s count_s*|table_s|^2 / (N*L): [S,L] math instead of [N,L]
-        key = (shape_index.data_ptr(), shape_index._version, shape_index.numel())
-        if self._counts_key != key:                      # points per shape: recomputed only when the index tensor changes
-            self._counts = torch.bincount(shape_index, minlength=self.table.shape[0]).to(torch.float32)
-            self._counts_key = key
-        counts = self._counts
+        # mean(z_batch^2) over the gathered rows == sum_s count_s*|table_s|^2 / (N*L): [S,L] math instead of [N,L].  The counts are
+        # recomputed from the index tensor on every call (no host sync, graph-capturable): a (data_ptr, _version, numel) key is not
+        # a tensor identity -- the caching allocator recycles addresses across the fresh index tensors of a data loader.
+        counts = torch.zeros(self.table.shape[0], dtype=torch.float32, device=points.device)
+        counts.index_add_(0, shape_index.long(), torch.ones((), dtype=torch.float32, device=points.device).expand(shape_index.shape[0]))
         reg = (counts.unsqueeze(1) * torch.pow(self.table, 2)).sum() / (points.shape[0] * self.table.shape[1])
         loss = torch.mean(torch.abs(out - sdf)) + self.sigma * reg     # :88
-        loss.backward()                                                # :89
+        with arena_backward():                                                # :89
+            loss.backward()
         self.nopt.step(); self.lopt.step()                              # :90-91
         return loss.detach()
 
@@ -211,7 +216,8 @@ class HybridProgressiveStep:
             q.requires_grad_(False)
         try:
             loss = -self.dis(self.generate(z)).mean()                                  # :143-144
-            loss.backward()
+            with arena_backward():
+                loss.backward()
         finally:
             for q in self.dopt.params:
                 q.requires_grad_(True)
@@ -227,7 +233,8 @@ class HybridProgressiveStep:
         out_fake, out_valid = out[:b], out[b:]
         gp = gradient_penalty(self.dis, valid, fake, alpha, self.gp_weight)            # :162
         loss = out_fake.mean() - out_valid.mean() + gp                                 # :163
-        loss.backward()
+        with arena_backward():
+            loss.backward()
         self.dopt.step()                                                               # :166
         return loss.detach(), gp.detach()
 
@@ -251,6 +258,7 @@ class VAEStep:
         diff = out - batch
         diff = torch.where(batch < 0, diff * 32, diff)                  # :57-62
         loss = torch.mean(torch.abs(diff)) + kld
-        loss.backward()
+        with arena_backward():
+            loss.backward()
         self.opt.step()
         return loss.detach()

@@ -142,3 +142,79 @@ def test_hybrid_progressive_step(it, fade):
     assert abs(g.item() - g_ref.item()) < 5e-3 * max(1.0, abs(g_ref.item()))
     params_close(dis, ref.d, 2.2e-3, 'progressive discriminator after RMSprop lr 1e-4')     # first RMSprop step = 10*lr
     params_close(gen, ref.g, 2.2e-3, 'SDFNet generator after RMSprop lr 1e-4')
+
+
+def _wgan_setup(seed_g=51, seed_c=52):
+    from model.gan import Discriminator, Generator
+    from shapegan_b200 import train
+    gen, cri = Generator(), Discriminator()
+    load(gen, TS.gen_shapes(), seed_g)
+    load(cri, TS.disc_shapes(), seed_c)
+    return gen, cri, train.WGANStep(gen, cri)
+
+
+def test_wgan_step_graph_replay_matches_eager():
+    """A captured WGANStep must re-pack the weight images INSIDE the graph: N replays == N eager steps, and a replay after the
+    critic's weights were zeroed behind the graph's back must see the zeros (a cached pre-capture image would not)."""
+    from shapegan_b200 import config
+    config.set_precision('bf16')
+    b = 4
+    real, z1, z2 = voxels(b, 32, 61).cuda(), rnd((b, 128), 62, -2, 2).cuda(), rnd((b, 128), 63, -2, 2).cuda()
+    gen_e, cri_e, step_e = _wgan_setup()
+    gen_g, cri_g, step_g = _wgan_setup()
+    losses = torch.zeros(2, device='cuda')
+
+    def body():
+        cl, gl = step_g(real, z1, z2)
+        losses[0].copy_(cl); losses[1].copy_(gl)
+    body()                                                    # eager warm-up step (also what bench.py does before capturing)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        body()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        body()
+    for _ in range(2):
+        step_e(real, z1, z2)
+    for _ in range(3):
+        graph.replay()
+        want = step_e(real, z1, z2)
+        torch.cuda.synchronize()
+        assert abs(losses[0].item() - want[0].item()) < 1e-5 + 1e-4 * abs(want[0].item())
+        assert abs(losses[1].item() - want[1].item()) < 1e-5 + 1e-4 * abs(want[1].item())
+    for m_g, m_e in ((gen_g, gen_e), (cri_g, cri_e)):
+        for (k, v), (_, w) in zip(m_g.state_dict().items(), m_e.state_dict().items()):
+            if 'num_batches' in k:
+                assert int(v) == int(w), k
+            else:
+                assert (v - w).abs().max().item() <= 1e-5, k
+    with torch.no_grad():
+        step_g.copt.flat.zero_()                              # every critic weight and bias := 0, behind the graph's back
+    graph.replay()
+    torch.cuda.synchronize()
+    assert losses[0].item() == 0.0, 'the replayed critic pass ran on a weight image packed before the capture'
+
+
+def test_autodecoder_step_fresh_index_tensors():
+    """The per-shape point counts of the 0.01*mean(z^2) term must follow the index tensor of THIS call, also when a data
+    loader hands over fresh tensors that the caching allocator places at a recycled address (train_sdf_autodecoder.py:77-80)."""
+    from model.sdf_net import SDFNet
+    from shapegan_b200 import train
+    n, shapes = 2048, 4
+    pts = rnd((n, 3), 71)
+    sdf = torch.clamp(pts.norm(dim=1) - 0.5, -0.1, 0.1)
+    table = rnd((shapes, 128), 72) * 0.5
+    net = SDFNet()
+    load(net, TS.sdf_shapes(), 73)
+    ref = S.AutodecoderStepCPU(S.make_params(TS.sdf_shapes(), 73), table)
+    step = train.AutodecoderStep(net, table.cuda())
+    for rep in range(3):
+        idx = ((torch.arange(n) * shapes) // n) if rep != 1 else torch.full((n,), 3, dtype=torch.int64)    # all points of shape 3
+        l_ref = ref(pts, sdf, idx)
+        idx_d = idx.to(torch.int32).cuda()                    # fresh device tensor each call; the previous one is freed
+        l = step(pts.cuda(), sdf.cuda(), idx_d)
+        del idx_d
+        assert abs(l.item() - l_ref.item()) < 2e-4 * max(1.0, abs(l_ref.item())), rep
+    assert (step.table.detach().cpu() - ref.table.detach()).abs().max().item() < 7e-5
