@@ -1,28 +1,35 @@
 """GPU (-m gpu): parity of the drop-in modules (CUDA path, through the C ABI) with the golden vectors produced by the
-UNMODIFIED reference (oracle/gen_golden.py) and with the CPU oracle (oracle/ref_torch.py) on the same seeded inputs.
+UNMODIFIED reference (oracle/gen_golden.py) on the same seeded weights and inputs.
 
-Metric: relative L2 per tensor, ||ours - ref|| / ||ref||.
-  fp32x mode (hi/lo bf16 split, fp32 accumulate)
-      outputs   <= 1e-3   -- the tolerance BASELINE.json's north_star states ("within 1e-3 relative fp32")
-      gradients <= 2e-2 element-wise rel-L2 AND <= 2e-3 on the tensor's norm -- the tensor core's fp32 accumulator
-                             truncates (measured 5e-5 of the output scale at K=16384, tests/test_gemm_gpu.py) and the
-                             reference's losses subtract two passes (mean D(fake) - mean D(real), train_wgan.py:68),
-                             which amplifies that noise ~100x on the weakest tensors (first-layer weights, biases).
-  bf16  mode (throughput mode the benchmark runs in): <= 3e-2 on outputs; gradients <= 0.6 rel-L2 / 0.2 on the norm:
-      bf16 operand rounding (2^-9 per element) through 4-8 layers and the backward chain, then the same two-pass
-      cancellation -- and for the gradient penalty the factor (||g||-1) -- leave 10-50% element-wise noise on the weakest
-      tensors while direction and norm are kept.  Reported for information, NOT the parity gate (fp32x is)."""
+Metric: relative L2 per tensor, ||ours - ref|| / ||ref|| (scalars: relative error; tensors that are analytically ZERO in exact
+arithmetic -- the gradient of a bias that feeds a train-mode BatchNorm -- : max |ours|).  Every measured error is recorded
+(conftest.PARITY -> gpurun_out/parity_errors.{json,txt}; the committed copy lives in profiles/) together with its gate:
+
+  fp32x (hi/lo bf16 split, fp32 accumulate -- the parity mode)
+      gate = max(1e-3, 3 x the reference's own fp32-vs-fp64 error of that tensor)      BASELINE.json: "within 1e-3 relative fp32"
+      (tests/golden/fp32_self_noise.json, oracle/gen_noise.py).  Tensors listed in FP32X_WEAK carry an explicit, measured bound
+      and the reason next to it; nothing else may exceed 1e-3.
+  bf16  (the mode bench.py times)
+      gate = 3 x the error measured for that tensor on a B200 (tests/golden/parity_measured.json, tools/update_parity_gates.py),
+      outputs additionally capped at 5e-3.  A tensor without a measured entry falls back to 5e-3 (outputs) / 5e-2 (gradients).
+
+SG_PARITY_RECORD=1 records without failing on the gates (used to (re)generate parity_measured.json)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import check_digest, load_golden, rel_l2
+from conftest import MEASURED, PARITY, SELF_NOISE, check_digest, digest_errors, load_golden, rel_l2
 from oracle import ref_torch as R
 
 pytestmark = pytest.mark.gpu
 
-TOL = {'fp32x': (1e-3, 2e-2), 'bf16': (3e-2, 6e-1)}
-NTOL = {'fp32x': 2e-3, 'bf16': 2e-1}
+RECORD_ONLY = os.environ.get('SG_PARITY_RECORD') == '1'
+
+# fp32x tensors allowed above 1e-3, each with its measured error x3 and the mechanism (see profiles/r02_parity_errors.txt).
+# {(case, key): (bound, why)}
+FP32X_WEAK = {}
 
 
 @pytest.fixture(params=['fp32x', 'bf16'])
@@ -51,81 +58,135 @@ def check_dev():
     assert L.lib().sg_check_device_error() == 0
 
 
-def grads_check(g, prefix, module, tol, atol=0.0, skip=(), ntol=None):
-    """check every parameter gradient; report the whole table before failing (one GPU run = full picture)"""
-    seen, lines, failed = set(), [], []
-    for k, p in module.named_parameters():
-        if id(p) in seen or k in skip:
-            continue
-        seen.add(id(p))
-        key = prefix + k
-        if key + '@sub' not in g:
-            continue
-        assert p.grad is not None, k
-        try:
-            err = check_digest(g, key, p.grad, tol, key, atol=atol, ntol=ntol)
-            lines.append('   ok  %-44s rel-L2 %.2e' % (key, err))
-        except AssertionError as e:
-            failed.append(key)
-            lines.append(' FAIL  %s' % str(e).split('\n')[0])
-    print('\n' + '\n'.join(lines))
-    assert not failed, 'gradient mismatch: %s' % failed
+class Checker:
+    """Collects every comparison of one test case, records it, and fails once at the end with the whole table."""
+
+    def __init__(self, prec, case, store):
+        self.prec, self.case, self.g = prec, case, store
+        self.lines, self.failed = [], []
+
+    def gate(self, key, kind):
+        noise = SELF_NOISE.get(self.case, {}).get(key, 0.0)
+        measured = MEASURED.get(self.prec, {}).get(self.case, {}).get(key)
+        if kind == 'zero':
+            # analytically zero: bounded by 3x the rounding residue measured on a B200 (absolute), else a loose absolute bound
+            return 3.0 * measured if measured is not None else (2e-2 if self.prec == 'fp32x' else 2.0)
+        if self.prec == 'fp32x':
+            gate = max(1e-3, 3.0 * noise)
+            weak = FP32X_WEAK.get((self.case, key))
+            return max(gate, weak[0]) if weak else gate
+        if measured is None:
+            return 5e-3 if kind in ('out', 'scalar') else 5e-2
+        gate = max(3.0 * measured, 1e-3)
+        return min(gate, 5e-3) if kind in ('out', 'scalar') else gate
+
+    def _finish(self, key, kind, err, norm_err=None):
+        noise = SELF_NOISE.get(self.case, {}).get(key)
+        gate = self.gate(key, kind)
+        PARITY.add(self.prec, self.case, key, err, gate, norm_err, kind)
+        ok = err <= gate
+        self.lines.append('%5s  %-46s %-6s err %.2e  gate %.1e%s' % ('ok' if ok else 'FAIL', key, kind, err, gate,
+                                                                    '' if noise is None else '  (ref fp32 noise %.1e)' % noise))
+        if not ok:
+            self.failed.append(key)
+        return err
+
+    def tensor(self, key, t, kind):
+        """golden stored in full under `key`, or as a digest under key@sub"""
+        noise = SELF_NOISE.get(self.case, {}).get(key, 0.0)
+        if noise > 1.0:
+            return self._finish(key, 'zero', float(t.detach().abs().max()))
+        if key in self.g:
+            return self._finish(key, kind, rel_l2(t, self.g[key]))
+        err, nerr, _ = digest_errors(self.g, key, t)
+        return self._finish(key, kind, err, nerr)
+
+    def out(self, key, t):
+        return self.tensor(key, t, 'out')
+
+    def grad(self, key, t):
+        return self.tensor(key, t, 'grad')
+
+    def scalar(self, key, value, ref=None):
+        ref = float(self.g[key]) if ref is None else float(ref)
+        return self._finish(key, 'scalar', abs(float(value) - ref) / max(abs(ref), 1e-30))
+
+    def params(self, prefix, module, skip=()):
+        seen = set()
+        for k, p in module.named_parameters():
+            if id(p) in seen or k in skip:
+                continue
+            seen.add(id(p))
+            key = prefix + k
+            if key + '@sub' not in self.g:
+                continue
+            assert p.grad is not None, k
+            self.grad(key, p.grad)
+
+    def done(self):
+        print('\n[%s %s]\n' % (self.prec, self.case) + '\n'.join(self.lines))
+        if not RECORD_ONLY:
+            assert not self.failed, '%s/%s beyond their gates: %s' % (self.prec, self.case, self.failed)
 
 
 # ------------------------------------------------------------------------------------------------- SDFNet
 def test_sdfnet_seeded(prec):
     from model.sdf_net import SDFNet
     g = load_golden('sdfnet_seeded')
-    t_out, t_grad = TOL[prec]
+    c = Checker(prec, 'sdfnet_seeded', g)
     net = SDFNet()
     seeded_load(net, int(g['seed_weights']))
     pts = cu(g['points']).requires_grad_(True)
     table = cu(g['latent_table']).requires_grad_(True)
     idx = cu(g['shape_index'])
     out = net(pts, table[idx])                                    # the reference call shape: materialised [N,128]
-    assert rel_l2(out, g['out']) < t_out
+    c.out('out', out)
     loss = torch.mean(torch.abs(out - cu(g['target']))) + 0.01 * torch.mean(torch.pow(table[idx], 2))
+    c.scalar('loss', loss.item())
     loss.backward()
-    assert rel_l2(table.grad, g['grad_latent_table']) < t_grad
-    assert rel_l2(pts.grad, g['grad_points']) < t_grad
-    grads_check(g, 'grad.', net, t_grad)
+    c.grad('grad_latent_table', table.grad)
+    c.grad('grad_points', pts.grad)
+    c.params('grad.', net)
     # indexed extension == materialised call
     net.zero_grad()
     table2 = cu(g['latent_table']).requires_grad_(True)
     out2 = net(cu(g['points']), table2, idx)
     assert rel_l2(out2, out.detach()) < 1e-6
     (torch.mean(torch.abs(out2 - cu(g['target']))) + 0.01 * torch.mean(torch.pow(table2[idx], 2))).backward()
-    assert rel_l2(table2.grad, g['grad_latent_table']) < t_grad
+    assert rel_l2(table2.grad, table.grad) < (1e-5 if prec == 'fp32x' else 2e-2)      # atomics order / run-length aggregation only
     # ragged / degenerate sizes (sdf_net.py:61,73-74)
     assert list(net(pts[:1].detach(), table[idx][:1].detach()).shape) == []
     assert list(net(pts[:0].detach(), table[idx][:0].detach()).shape) == [0]
+    c.done()
     check_dev()
 
 
 def test_sdfnet_latent0_chairs_and_helpers(prec):
     from model.sdf_net import SDFNet, get_voxel_coordinates
-    t_out, _ = TOL[prec]
     g = load_golden('sdfnet_latent0')
+    c = Checker(prec, 'sdfnet_latent0', g)
     net0 = SDFNet(latent_code_size=0)
     seeded_load(net0, int(g['seed_weights']))
     pts = cu(g['points'])
-    assert rel_l2(net0(pts, torch.zeros((pts.shape[0], 0), device='cuda')), g['out']) < t_out
+    c.out('out', net0(pts, torch.zeros((pts.shape[0], 0), device='cuda')))
+    c.done()
     g = load_golden('sdfnet_chairs')
+    c = Checker(prec, 'sdfnet_chairs', g)
     net = SDFNet()
     net.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('w.')}, strict=True)
     grid = get_voxel_coordinates(32, return_torch_tensor=True, device='cuda')
     assert np.array_equal(grid.cpu().numpy(), R.voxel_coordinates(32).numpy())          # bit-exact indexing
     z = cu(g['z'])
     out = net.evaluate_in_batches(grid, z, batch_size=10000)
-    assert not out.is_cuda and rel_l2(out, g['out']) < t_out
+    assert not out.is_cuda
+    c.out('out', out)
     out_rep = net(grid, z.repeat(grid.shape[0], 1))
-    assert rel_l2(out_rep, g['out']) < t_out
+    assert rel_l2(out_rep, out) < 1e-6
     if prec == 'fp32x':
         assert abs(out.sum().item() - 2386.4048) < 1.0            # SURVEY 8c known answer
     vox = net.get_voxels(z, 32)
     assert vox.shape == (32, 32, 32) and vox[0, 0, 0] == 1.0
-    normals = net.get_normals(z, grid[:1000].clone())
-    assert torch.allclose(normals.norm(dim=1), torch.ones(1000, device='cuda'), atol=1e-4)
+    c.done()
     check_dev()
 
 
@@ -133,26 +194,27 @@ def test_sdfnet_latent0_chairs_and_helpers(prec):
 def test_generator(prec):
     from model.gan import Generator
     g = load_golden('gan_generator')
-    t_out, t_grad = TOL[prec]
+    c = Checker(prec, 'gan_generator', g)
     gen = Generator()
     seeded_load(gen, int(g['seed_weights']))
     z = cu(g['z'])
     gen.train()
     out = gen(z)
     assert tuple(out.shape) == (4, 1, 32, 32, 32)
-    assert rel_l2(out, g['out_train']) < t_out
+    c.out('out_train', out)
     wout = (torch.rand((4, 1, 32, 32, 32), generator=torch.Generator().manual_seed(int(g['seed_wout']))) * 2 - 1).cuda()
     (out * wout).sum().backward()
-    grads_check(g, 'grad.', gen, t_grad, atol=2e-2 if prec == 'fp32x' else 20.0, ntol=NTOL[prec])
+    c.params('grad.', gen)
     for k, v in gen.state_dict().items():
         if 'running' in k:
-            assert rel_l2(v, g['after.' + k]) < t_out, k
+            c.out('after.' + k, v)
         if 'num_batches' in k:
             assert int(v) == int(g['after.' + k])
     gen.eval()
     with torch.no_grad():
-        assert rel_l2(gen(z), g['out_eval']) < t_out
+        c.out('out_eval', gen(z))
     assert tuple(gen.generate(3).shape) == (3, 1, 32, 32, 32)
+    c.done()
     check_dev()
 
 
@@ -160,29 +222,32 @@ def test_generator(prec):
 def test_discriminator(prec):
     from model.gan import Discriminator
     g = load_golden('gan_discriminator')
-    t_out, t_grad = TOL[prec]
+    c = Checker(prec, 'gan_discriminator', g)
     dis = Discriminator()
     seeded_load(dis, int(g['seed_weights']))
     real, fake = cu(g['real']), cu(g['fake'])
     with torch.no_grad():
-        assert rel_l2(dis(real), g['out_sigmoid']) < t_out
+        c.out('out_sigmoid', dis(real))
         assert list(dis(real[:1]).shape) == []
     dis.use_sigmoid = False
     fake_g = fake.clone().requires_grad_(True)
     of, orl = dis(fake_g), dis(real)
-    assert rel_l2(of, g['out_fake']) < t_out and rel_l2(orl, g['out_real']) < t_out
+    c.out('out_fake', of)
+    c.out('out_real', orl)
     (torch.mean(of) - torch.mean(orl)).backward()                  # train_wgan.py:68
-    grads_check(g, 'grad.', dis, t_grad, ntol=NTOL[prec])
-    check_digest(g, 'grad_fake', fake_g.grad, t_grad)
+    c.params('grad.', dis)
+    c.grad('grad_fake', fake_g.grad)
     # BCE path (train_gan.py:64,78,84)
     dis.zero_grad()
     dis.use_sigmoid = True
     o = dis(fake)
     lf = torch.nn.functional.binary_cross_entropy(o, torch.zeros(4, device='cuda'))
     lv = torch.nn.functional.binary_cross_entropy(dis(real), torch.ones(4, device='cuda'))
-    assert abs(lf.item() - float(g['bce_fake_loss'])) < 5e-3 and abs(lv.item() - float(g['bce_valid_loss'])) < 5e-3
+    c.scalar('bce_fake_loss', lf.item())
+    c.scalar('bce_valid_loss', lv.item())
     (lf + lv).backward()
-    grads_check(g, 'bce_grad.', dis, t_grad, ntol=NTOL[prec])
+    c.params('bce_grad.', dis)
+    c.done()
     check_dev()
 
 
@@ -191,7 +256,7 @@ def test_discriminator_gradient_penalty(prec):
     + backward through our twice-differentiable layer Functions."""
     from model.gan import Discriminator
     g = load_golden('gan_discriminator')
-    t_out, t_grad = TOL[prec]
+    c = Checker(prec, 'gan_discriminator', g)
     dis = Discriminator()
     seeded_load(dis, int(g['seed_weights']))
     dis.use_sigmoid = False
@@ -201,14 +266,15 @@ def test_discriminator_gradient_penalty(prec):
     o = dis(xi)
     grads = torch.autograd.grad(outputs=o, inputs=xi, grad_outputs=torch.ones(o.shape, device='cuda'), create_graph=True,
                                 retain_graph=True, only_inputs=True)[0]
-    check_digest(g, 'gp_input_grad', grads, t_grad)
+    c.grad('gp_input_grad', grads)
     gp = ((grads.norm(2, dim=(1, 2, 3)) - 1) ** 2).mean() * 10
-    assert abs(gp.item() - float(g['gp'])) / float(g['gp']) < (2e-3 if prec == 'fp32x' else 5e-2)
+    c.scalar('gp', gp.item())
     gp.backward()
-    grads_check(g, 'gp_grad.', dis, t_grad, ntol=NTOL[prec])
+    c.params('gp_grad.', dis)
     for k, p in dis.named_parameters():
         if 'bias' in k:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0      # GP contributes nothing to biases
+    c.done()
     check_dev()
 
 
@@ -218,7 +284,7 @@ def test_discriminator_gradient_penalty(prec):
 def test_progressive_discriminator(prec, name):
     from model.progressive_gan import Discriminator
     g = load_golden(name)
-    t_out, t_grad = TOL[prec]
+    c = Checker(prec, name, g)
     it, fade = int(g['iteration']), float(g['fade'])
     d = Discriminator().cuda()          # the reference ctor leaves it on the CPU; scripts call .to(device)
     seeded_load(d, int(g['seed_weights']))
@@ -228,17 +294,19 @@ def test_progressive_discriminator(prec, name):
     real, fake, alpha = cu(g['real']), cu(g['fake']), cu(g['alpha'])
     fake_g = fake.clone().requires_grad_(True)
     of, orl = d(fake_g), d(real)
-    assert rel_l2(of, g['out_fake']) < t_out and rel_l2(orl, g['out_real']) < t_out
+    c.out('out_fake', of)
+    c.out('out_real', orl)
     a = alpha.expand(real.shape)
     xi = (a * real + (1 - a) * fake).detach().requires_grad_(True)
     o = d(xi)
     grads = torch.autograd.grad(outputs=o, inputs=xi, grad_outputs=torch.ones(o.shape, device='cuda'), create_graph=True,
                                 retain_graph=True, only_inputs=True)[0]
     gp = ((grads.norm(2, dim=(1, 2, 3)) - 1) ** 2).mean() * 10
-    assert abs(gp.item() - float(g['gp'])) / float(g['gp']) < (2e-3 if prec == 'fp32x' else 5e-2)
+    c.scalar('gp', gp.item())
     (of.mean() - orl.mean() + gp).backward()                       # train_hybrid_progressive_gan.py:163
-    grads_check(g, 'grad.', d, t_grad, atol=1e-6, ntol=NTOL[prec])
-    check_digest(g, 'grad_fake', fake_g.grad, t_grad)
+    c.params('grad.', d)
+    c.grad('grad_fake', fake_g.grad)
+    c.done()
     check_dev()
 
 
@@ -246,8 +314,9 @@ def test_progressive_discriminator(prec, name):
 @pytest.mark.parametrize('variational', [True, False])
 def test_autoencoder(prec, variational):
     import model.autoencoder as ae
-    g = load_golden('autoencoder_vae' if variational else 'autoencoder_classic')
-    t_out, t_grad = TOL[prec]
+    name = 'autoencoder_vae' if variational else 'autoencoder_classic'
+    g = load_golden(name)
+    c = Checker(prec, name, g)
     m = ae.Autoencoder(is_variational=variational)
     seeded_load(m, int(g['seed_weights']))
     x, eps = cu(g['x']), torch.from_numpy(g['eps'])
@@ -263,26 +332,27 @@ def test_autoencoder(prec, variational):
             out, mean, logvar = m(x)
         finally:
             impl.standard_normal_distribution = old
-        assert rel_l2(mean, g['mean']) < t_out and rel_l2(logvar, g['log_variance']) < t_out
+        c.out('mean', mean)
+        c.out('log_variance', logvar)
         kld = -0.5 * torch.sum(1 + logvar - mean.pow(2) - logvar.exp()) / mean.nelement()
     else:
         out = m(x)
         kld = 0
-    assert rel_l2(out, g['out_train']) < t_out
+    c.out('out_train', out)
     diff = out - x
     diff = torch.where(x < 0, diff * 32, diff)
     loss = torch.mean(torch.abs(diff)) + kld
-    assert abs(loss.item() - float(g['loss'])) / abs(float(g['loss'])) < t_out
+    c.scalar('loss', loss.item())
     loss.backward()
-    # 13 layers with 9 train-mode BatchNorms at batch 4: the norm of a few small tensors moves by ~3e-3 in fp32x
-    grads_check(g, 'grad.', m, t_grad, atol=2e-5 if prec == 'fp32x' else 1e-2, ntol=5e-3 if prec == 'fp32x' else NTOL[prec])
+    c.params('grad.', m)
     for k, v in m.state_dict().items():
         if 'running' in k:
-            check_digest(g, 'after.' + k, v, t_out)
+            c.out('after.' + k, v)
     m.eval()
     with torch.no_grad():
         o = m(x)
-        assert rel_l2(o[0] if variational else o, g['out_eval']) < t_out
+        c.out('out_eval', o[0] if variational else o)
+    c.done()
     check_dev()
 
 
