@@ -147,6 +147,19 @@ def run_cases(mods, dt):
         o['out_train'], o['loss'] = out, loss.reshape(1)
         grads(m, 'grad.', o)
         res['autoencoder_%s' % ('vae' if variational else 'classic')] = o
+    # ---- wgan_step_b64: critic pass of train_wgan.py:65-69 at BASELINE configs[1]'s batch (keys of tests/golden/wgan_step_b64.npz)
+    o = {}
+    bq = 64
+    gen, cri = load(gan.Generator(), 601, dt), load(gan.Discriminator(), 602, dt)
+    cri.use_sigmoid = False
+    z1, batch = c(rnd((bq, 128), 743, -2, 2)), c(synth_voxels(bq, 32, 745))
+    gen.train()
+    fake = gen(z1).detach()
+    closs = torch.mean(cri(fake)) - torch.mean(cri(batch))
+    closs.backward()
+    o['critic_loss'] = closs.reshape(1)
+    grads(cri, 'critic_grad.', o)
+    res['wgan_step_b64'] = o
     return res
 
 

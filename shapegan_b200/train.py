@@ -140,9 +140,17 @@ class GANStep:
         gen, dis = self.gen, self.dis
         b = real.shape[0]
         self.gopt.zero_grad(); self.dopt.zero_grad()
-        gloss = -torch.mean(torch.log(dis(gen(z_gen))))                # :61-65
-        with arena_backward():
-            gloss.backward()
+        # :61-65.  The reference's backward here also fills the discriminator's weight gradients, which :74 zeroes unread: same
+        # update without that dead work (the discriminator parameters do not require grad during this backward).
+        for q in self.dopt.params:
+            q.requires_grad_(False)
+        try:
+            gloss = -torch.mean(torch.log(dis(gen(z_gen))))
+            with arena_backward():
+                gloss.backward()
+        finally:
+            for q in self.dopt.params:
+                q.requires_grad_(True)
         self.gopt.step()
         self.dopt.zero_grad()
         with torch.no_grad():

@@ -11,7 +11,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(extra_env, *args):
     env = dict(os.environ)
     env.update(extra_env)
-    return subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1', *args],
+    return subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--batch', '4', *args],
                           capture_output=True, text=True, timeout=600, env=env, cwd=REPO)
 
 
@@ -26,7 +26,8 @@ def test_reference_arm_json_contract():
     assert d['config']['workload'].startswith('configs[1]')           # same workload string as the B200 arm
     assert d['e2e'] == {'value': d['value'], 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'B=8' in cb['sample']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'full B=4 step' in cb['sample']
+    assert 'WGAN-GP' in d['config']['workload'] and d['config']['global_batch'] == 4      # default workload = BASELINE configs[1]
 
 
 def test_reference_arm_prints_on_rank0_only():

@@ -533,3 +533,52 @@ def test_wgan_step_flat_optimizer(prec):
     # a second step must run (arena views, version bumps, pack-cache invalidation)
     step(cu(g['batch']), cu(g['z_critic']), cu(g['z_gen']))
     check_dev()
+
+
+# ------------------------------------------------------------------------------------------------- BASELINE batch size (B=64)
+def test_wgan_critic_pass_b64(prec):
+    """train_wgan.py:65-69 at BASELINE configs[1]'s batch (64): critic loss and every critic gradient against the reference's B=64
+    digests (tests/golden/wgan_step_b64.npz) -- the full-size counterpart of the B=4 goldens."""
+    from model.gan import Discriminator, Generator
+    from oracle.gen_golden import rnd, synth_voxels
+    g = load_golden('wgan_step_b64')
+    c = Checker(prec, 'wgan_step_b64', g)
+    b = int(g['batch_size'])
+    gen, cri = Generator(), Discriminator()
+    seeded_load(gen, 601)
+    seeded_load(cri, 602)
+    cri.use_sigmoid = False
+    z1, batch = rnd((b, 128), int(g['seed_z_critic']), -2, 2).cuda(), synth_voxels(b, 32, int(g['seed_batch'])).cuda()
+    gen.train()
+    fake = gen(z1).detach()
+    closs = torch.mean(cri(fake)) - torch.mean(cri(batch))
+    closs.backward()
+    c.scalar('critic_loss', closs.item())
+    c.params('critic_grad.', cri)
+    c.done()
+    check_dev()
+
+
+def test_wgan_step_object_b64(prec):
+    """shapegan_b200.train.WGANStep (what bench.py times) at B=64 against the reference's step digest: losses, and the updated
+    weights to the absolute bound of RMSprop's sign-like first step (tests/test_ref_steps_golden.py explains the bound)."""
+    from model.gan import Discriminator, Generator
+    from oracle.gen_golden import rnd, synth_voxels
+    from shapegan_b200 import train
+    g = load_golden('wgan_step_b64')
+    b = int(g['batch_size'])
+    gen, cri = Generator(), Discriminator()
+    seeded_load(gen, 601)
+    seeded_load(cri, 602)
+    step = train.WGANStep(gen, cri)
+    z1, z2 = rnd((b, 128), int(g['seed_z_critic']), -2, 2).cuda(), rnd((b, 128), int(g['seed_z_gen']), -2, 2).cuda()
+    closs, gloss = step(synth_voxels(b, 32, int(g['seed_batch'])).cuda(), z1, z2)
+    tol = 1e-3 if prec == 'fp32x' else 5e-3
+    assert abs(closs.item() - float(g['critic_loss'])) <= tol * max(1.0, abs(float(g['critic_loss'])))
+    assert abs(gloss.item() - float(g['generator_loss'])) <= tol * max(1.0, abs(float(g['generator_loss'])))
+    for k, v in gen.state_dict().items():
+        if 'num_batches' not in k:
+            check_digest(g, 'gen_after.' + k, v, 1e-3 if prec == 'fp32x' else 1e-2, atol=1.1e-3)
+    for k, v in cri.state_dict().items():
+        check_digest(g, 'critic_after.' + k, v, 1e-3 if prec == 'fp32x' else 1e-2, atol=1.1e-3)
+    check_dev()

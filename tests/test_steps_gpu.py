@@ -218,3 +218,92 @@ def test_autodecoder_step_fresh_index_tensors():
         del idx_d
         assert abs(l.item() - l_ref.item()) < 2e-4 * max(1.0, abs(l_ref.item())), rep
     assert (step.table.detach().cpu() - ref.table.detach()).abs().max().item() < 7e-5
+
+
+# ------------------------------------------------------------------------------------------------- step objects vs the reference's step goldens
+def _after_close(g, prefix, module, atol):
+    import numpy as np
+    from conftest import digest_errors
+    worst, n = 0.0, 0
+    for k, v in module.state_dict().items():
+        if prefix + k + '@sub' not in g:
+            continue
+        _, _, maxabs = digest_errors(g, prefix + k, v)
+        worst, n = max(worst, maxabs), n + 1
+    assert n > 0 and worst <= atol, '%s: max deviation %.3e > %.1e over %d tensors' % (prefix, worst, atol, n)
+    return np.float64(worst)
+
+
+def test_gan_step_vs_reference_golden():
+    """train_gan.py:58-86 golden from the unmodified reference (oracle/gen_golden_steps.py)."""
+    from conftest import load_golden
+    from model.gan import Discriminator, Generator
+    from shapegan_b200 import train
+    g = load_golden('gan_step')
+    gen, dis = Generator(), Discriminator()
+    load(gen, TS.gen_shapes(), 701)
+    load(dis, TS.disc_shapes(), 702)
+    got = train.GANStep(gen, dis)(torch.from_numpy(g['real']).cuda(), torch.from_numpy(g['z_gen']).cuda(), torch.from_numpy(g['z_dis']).cuda())
+    for a, c in zip(got, g['losses']):
+        assert abs(a.item() - float(c)) < 2e-3 * max(1.0, abs(float(c)))
+    _after_close(g, 'gen_after.', gen, 2.2e-3)               # Adam lr 1e-3: the first step moves every weight by ~lr
+    _after_close(g, 'dis_after.', dis, 4.4e-5)               # two Adam steps of lr 1e-5
+
+
+@pytest.mark.parametrize('variational', [True, False])
+def test_vae_step_vs_reference_golden(variational):
+    import shapegan_b200.nn.autoencoder as impl
+    from conftest import load_golden
+    from model.autoencoder import Autoencoder
+    from shapegan_b200 import train
+    g = load_golden('vae_step_%s' % ('vae' if variational else 'classic'))
+    m = Autoencoder(is_variational=variational)
+    load(m, TS.ae_shapes(variational), 711 + int(variational))
+    eps = torch.from_numpy(g['eps'])
+
+    class _Fixed:
+        def sample(self, shape):
+            return eps.reshape(shape)
+    old = impl.standard_normal_distribution
+    impl.standard_normal_distribution = _Fixed()
+    try:
+        got = train.VAEStep(m)(torch.from_numpy(g['x']).cuda())
+    finally:
+        impl.standard_normal_distribution = old
+    assert abs(got.item() - float(g['loss'])) < 2e-3 * max(1.0, abs(float(g['loss'])))
+    _after_close(g, 'after.', m, 1.1e-4)                     # Adam lr 5e-5
+
+
+def test_autodecoder_step_vs_reference_golden():
+    from conftest import load_golden
+    from model.sdf_net import SDFNet
+    from shapegan_b200 import train
+    g = load_golden('autodecoder_step')
+    net = SDFNet()
+    load(net, TS.sdf_shapes(), 721)
+    step = train.AutodecoderStep(net, torch.from_numpy(g['latent_table']).cuda())
+    pts, sdf, idx = (torch.from_numpy(g[k]).cuda() for k in ('points', 'sdf', 'shape_index'))
+    for want in g['losses']:
+        got = step(pts, sdf, idx.to(torch.int32))
+        assert abs(got.item() - float(want)) < 2e-4 * max(1.0, abs(float(want)))
+    _after_close(g, 'after.', net, 4.5e-5)                   # two Adam steps of lr 1e-5
+    assert (step.table.detach().cpu() - torch.from_numpy(g['latent_table_after'])).abs().max().item() < 4.5e-5
+
+
+def test_hybrid_step_vs_reference_golden():
+    from conftest import load_golden
+    from model.progressive_gan import Discriminator
+    from model.sdf_net import SDFNet
+    from shapegan_b200 import train
+    g = load_golden('hybrid_step_it1')
+    gen, dis = SDFNet(), Discriminator().cuda()
+    load(gen, TS.sdf_shapes(), 731)
+    load(dis, TS.prog_shapes(), 732)
+    dis.fade_in_progress = float(g['fade'])
+    step = train.HybridProgressiveStep(gen, dis, int(g['iteration']))
+    dl, gp = step.discriminator_update(torch.from_numpy(g['valid']).cuda(), torch.from_numpy(g['z_dis']).cuda(), torch.from_numpy(g['alpha']).cuda())
+    gl = step.generator_update(torch.from_numpy(g['z_gen']).cuda())
+    for a, c in zip((dl, gp, gl), g['losses']):
+        assert abs(a.item() - float(c)) < 5e-3 * max(1.0, abs(float(c)))
+    _after_close(g, 'dis_after.', dis, 2.2e-3)               # first RMSprop step = 10 lr = 1e-3 per weight
+    _after_close(g, 'gen_after.', gen, 2.2e-3)

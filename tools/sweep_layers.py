@@ -1,12 +1,13 @@
-"""Time every GEMM shape of the WGAN G+D step (B=64, bf16) under different tile configurations.
-   python tools/sweep_layers.py > gpurun_out/sweep.txt"""
+"""Time every GEMM shape of the WGAN G+D step (bf16) in its AUTO tile configuration, B=64 and the batched critic's B=128;
+extra (bn, mt, ksplit) triples can be appended as arguments "bn,mt,ks" to compare against auto.
+   python tools/sweep_layers.py [bn,mt,ks ...] > gpurun_out/sweep.txt"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from shapegan_b200 import _lib as L, raw
 
-B = 64
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+CONFIGS = [(0, 0, 0)] + [tuple(int(v) for v in a.split(',')) for a in sys.argv[1:]]
 
 
 def timeit(fn, reps=8):
@@ -28,48 +29,40 @@ def bf(shape):
     return torch.randn((1,) + shape, device='cuda').to(torch.bfloat16)
 
 
-def conv_fwd(r, cin, cout):
+def conv_fwd(B, r, cin, cout):
     x = bf((B, r, r, r, cin)); w = torch.randn((cout, cin, 4, 4, 4), device='cuda') * 0.05
     img = raw.pack_conv_fwd(w, 1); ro = r // 2; rows = B * ro ** 3
     y = torch.empty((1, rows, cout), dtype=torch.bfloat16, device='cuda')
     fl = 2.0 * rows * cout * 64 * cin
-    return lambda bn, mt: raw.igemm(L.MODE_CONV, 1, x, (B, r, r, r, cin), rows, 64 * cin, img, cout, y, cout, act=L.ACT_LRELU, bn=bn, mt=mt), fl
+    return lambda bn, mt, ks: raw.igemm(L.MODE_CONV, 1, x, (B, r, r, r, cin), rows, 64 * cin, img, cout, y, cout, act=L.ACT_LRELU, bn=bn, mt=mt, ksplit=ks), fl
 
 
-def convt_fwd(r, cin, cout):          # also == conv dgrad with roles swapped
+def convt_fwd(B, r, cin, cout):          # also == conv dgrad with roles swapped
     x = bf((B, r, r, r, cin)); w = torch.randn((cin, cout, 4, 4, 4), device='cuda') * 0.05
     img = raw.pack_convt_fwd(w, 1); ro = 2 * r
     y = torch.empty((1, B * ro ** 3, cout), dtype=torch.bfloat16, device='cuda')
     fl = 2.0 * B * r ** 3 * 8 * cout * 8 * cin
-    return lambda bn, mt: raw.igemm(L.MODE_CONVT, 1, x, (B, r, r, r, cin), B * r ** 3, 8 * cin, img, cout, y, cout, out_dims=(ro, ro, ro), bn=bn, mt=mt), fl
+    return lambda bn, mt, ks: raw.igemm(L.MODE_CONVT, 1, x, (B, r, r, r, cin), B * r ** 3, 8 * cin, img, cout, y, cout, out_dims=(ro, ro, ro), bn=bn, mt=mt, ksplit=ks), fl
 
 
-def wgrad_conv(r, cin, cout):
+def wgrad_conv(B, r, cin, cout):
     x = bf((B, r, r, r, cin)); ro = r // 2; dy = bf((B, ro, ro, ro, cout)); rows = B * ro ** 3
     g = torch.zeros((cout, cin, 4, 4, 4), device='cuda')
     fl = 2.0 * rows * cout * 64 * cin
-    return lambda ks, mg: raw.wgrad(L.MODE_CONV, 1, dy, cout, x, (B, r, r, r, cin), rows, g, sm=cin * 64, st=1, sc=64, m_valid=cout, merge_n=mg, ksplit=ks), fl
+    return lambda bn, mt, ks: raw.wgrad(L.MODE_CONV, 1, dy, cout, x, (B, r, r, r, cin), rows, g, sm=cin * 64, st=1, sc=64, m_valid=cout, merge_n=1, ksplit=ks), fl
 
 
 print('torch', torch.__version__, torch.cuda.get_device_name(0))
-layers = [('conv 64->128 16^3 (D2)', conv_fwd(16, 64, 128)), ('conv 128->256 8^3 (D3)', conv_fwd(8, 128, 256)),
-          ('convT 256->128 4^3 (G2 / D3 dgrad)', convt_fwd(4, 256, 128)), ('convT 128->64 8^3 (G3 / D2 dgrad)', convt_fwd(8, 128, 64)),
-          ('conv 128->256 from dY 8^3 (G2 dgrad)', conv_fwd(8, 128, 256)), ('conv 64->128 from dY 16^3 (G3 dgrad)', conv_fwd(16, 64, 128))]
-for name, (fn, fl) in layers:
-    print('== %s  %.2f GFLOP' % (name, fl / 1e9))
-    for bn in (0, 64, 128, 256):
-        for mt in (0, 1, 2):
+for B in (64, 128):
+    layers = [('conv 64->128 16^3 (D2 fwd / G3 dgrad)', conv_fwd(B, 16, 64, 128)), ('conv 128->256 8^3 (D3 fwd / G2 dgrad)', conv_fwd(B, 8, 128, 256)),
+              ('convT 256->128 4^3 (G2 fwd / D3 dgrad)', convt_fwd(B, 4, 256, 128)), ('convT 128->64 8^3 (G3 fwd / D2 dgrad)', convt_fwd(B, 8, 128, 64)),
+              ('wgrad conv 64->128 16^3 (D2 / G3)', wgrad_conv(B, 16, 64, 128)), ('wgrad conv 128->256 8^3 (D3 / G2)', wgrad_conv(B, 8, 128, 256))]
+    for name, (fn, fl) in layers:
+        for bn, mt, ks in CONFIGS:
+            if 'wgrad' in name and (bn, mt, ks) != (0, 0, 0):
+                continue
             try:
-                us = timeit(lambda: fn(bn, mt))
-                print('   bn=%3d mt=%d  %8.1f us  %7.1f TFLOP/s' % (bn, mt, us, fl / us / 1e6))
+                us = timeit(lambda: fn(bn, mt, ks))
+                print('B=%3d %-42s %6.2f GFLOP  bn=%3d mt=%d ks=%d  %8.1f us  %7.1f TFLOP/s' % (B, name, fl / 1e9, bn, mt, ks, us, fl / us / 1e6))
             except Exception as e:
-                print('   bn=%3d mt=%d  -- %s' % (bn, mt, str(e)[:60]))
-for name, (fn, fl) in [('wgrad conv 64->128 16^3', wgrad_conv(16, 64, 128)), ('wgrad conv 128->256 8^3', wgrad_conv(8, 128, 256))]:
-    print('== %s  %.2f GFLOP' % (name, fl / 1e9))
-    for ks in (0, 2, 4, 8, 16):
-        for mg in (0, 1):
-            try:
-                us = timeit(lambda: fn(ks, mg))
-                print('   ksplit=%2d merge=%d  %8.1f us  %7.1f TFLOP/s' % (ks, mg, us, fl / us / 1e6))
-            except Exception as e:
-                print('   ksplit=%2d merge=%d -- %s' % (ks, mg, str(e)[:60]))
+                print('B=%3d %-42s bn=%3d mt=%d ks=%d -- %s' % (B, name, bn, mt, ks, str(e)[:80]))
