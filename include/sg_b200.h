@@ -71,8 +71,13 @@ typedef struct {
   int64_t out_plane_stride;
   int32_t out_kind, out_ld;
   int32_t out_d, out_h, out_w; /* SG_MODE_CONVT: output grid (2d,2h,2w) */
+  void* splitk_ws;             /* optional fp32 workspace for split-K with a non-atomic output: [ksplit][out rows][n_pad]; the K splits
+                                  store partial slabs, a finish kernel sums them and applies bias / act / mask.  NULL = never split. */
+  int64_t splitk_ws_bytes;
 } sg_igemm_args;
 int sg_igemm(const sg_igemm_args* a, void* stream);
+/* bytes of splitk_ws sg_igemm would use for `a` (0 = it will not split K): few output tiles x long K, e.g. Conv3d(128->256) 8^3->4^3 */
+int sg_igemm_plan(const sg_igemm_args* a, size_t* ws_bytes);
 
 /* dW partials: P[split][m, n] = sum_rows A[row, m] * gather(B)[row (+tap), n]
  * replaces: the weight-gradient (bwd-filter) calls autograd issues for the layers above.

@@ -23,7 +23,8 @@ class SgIgemmArgs(ctypes.Structure):
                 ('b_packed', c_void_p), ('bias', c_void_p), ('act', c_int32), ('bias_mod', c_int32),
                 ('mask', c_void_p), ('mask_plane_stride', c_int64), ('mask_act', c_int32),
                 ('out', c_void_p), ('out_plane_stride', c_int64), ('out_kind', c_int32), ('out_ld', c_int32),
-                ('out_d', c_int32), ('out_h', c_int32), ('out_w', c_int32)]
+                ('out_d', c_int32), ('out_h', c_int32), ('out_w', c_int32),
+                ('splitk_ws', c_void_p), ('splitk_ws_bytes', c_int64)]
 
 
 class SgWgradArgs(ctypes.Structure):
@@ -65,6 +66,7 @@ SYMBOLS = {
     'sg_stream_capture_id': (c_int32, [c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]),
     'sg_debug_igemm_trace': (c_int32, [ctypes.POINTER(c_longlong), c_int32]),
     'sg_igemm': (c_int32, [ctypes.POINTER(SgIgemmArgs), c_void_p]),
+    'sg_igemm_plan': (c_int32, [ctypes.POINTER(SgIgemmArgs), ctypes.POINTER(c_size_t)]),
     'sg_wgrad_plan': (c_int32, [ctypes.POINTER(SgWgradArgs), ctypes.POINTER(c_size_t)]),
     'sg_wgrad': (c_int32, [ctypes.POINTER(SgWgradArgs), c_void_p]),
     'sg_wgrad_reduce': (c_int32, [ctypes.POINTER(SgWgradReduceArgs), c_void_p]),

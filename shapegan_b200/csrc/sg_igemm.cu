@@ -37,6 +37,7 @@ struct IgemmP {
   const float* bias; int act, bias_mod;
   const bf16* mask; long long mask_ps; int mask_act;
   char* out; long long out_ps; int out_kind, out_ld, oD, oH, oW;
+  long long ks_stride;   // elements between the fp32 partial slabs of consecutive K splits (0: atomics / no split)
   int stages, m_tiles, n_tiles; long long work_total;
   int diag;              // measurement only (SG_B200_IGEMM_DIAG): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip the epilogue stores,
                          // 16 skip the whole K loop and epilogue (launch + prologue + teardown only)
@@ -85,7 +86,7 @@ __device__ __forceinline__ float act_t(float v, int runtime_act) {
 struct EpiP {   // the fields the epilogue needs, copied ONCE into registers: the kernel parameter is reached through a
                 // reference here, and every p.field access would otherwise be a generic load with a long-scoreboard stall
   int mode, planes, n_valid, bn, mt, ksplit, m_tiles, n_tiles, bias_mod, act, mask_act, out_kind, out_ld, oD, oH, oW, aD, aH, aW, acc_bufs, acc_slot;
-  long long rows, work_total, out_ps;
+  long long rows, work_total, out_ps, ks_stride;
   const float* bias; const bf16* mask; char* out; int* err;
 };
 
@@ -95,7 +96,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
   p.mode = gp.mode; p.planes = gp.planes; p.n_valid = gp.n_valid; p.bn = gp.bn; p.mt = gp.mt; p.ksplit = gp.ksplit;
   p.m_tiles = gp.m_tiles; p.n_tiles = gp.n_tiles; p.bias_mod = gp.bias_mod; p.act = gp.act; p.mask_act = gp.mask_act;
   p.out_kind = gp.out_kind; p.out_ld = gp.out_ld; p.oD = gp.oD; p.oH = gp.oH; p.oW = gp.oW; p.aD = gp.aD; p.aH = gp.aH; p.aW = gp.aW;
-  p.acc_bufs = gp.acc_bufs; p.acc_slot = gp.acc_slot; p.rows = gp.rows; p.work_total = gp.work_total; p.out_ps = gp.out_ps;
+  p.acc_bufs = gp.acc_bufs; p.acc_slot = gp.acc_slot; p.rows = gp.rows; p.work_total = gp.work_total; p.out_ps = gp.out_ps; p.ks_stride = gp.ks_stride;
   p.bias = gp.bias; p.mask = gp.mask; p.out = gp.out; p.err = gp.err;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -134,7 +135,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
         orow = ((n * p.oD + 2 * qd + ((cls >> 2) & 1)) * p.oH + 2 * qh + ((cls >> 1) & 1)) * p.oW + 2 * qw + (cls & 1);
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
-      const long long obase = orow * p.out_ld + (long long)nt * p.bn;
+      const long long obase = orow * p.out_ld + (long long)nt * p.bn + (long long)ks * p.ks_stride;   // ks_stride: split-K partial slabs
       if (fast) {
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
           uint32_t r[32];
@@ -806,6 +807,129 @@ static int igemm_validate(const sg_igemm_args* a) {
   return 0;
 }
 
+
+// ================================================================================================ split-K finish
+// out[row, n] = act( sum_s P[s][row][n] + bias[n] ) (* act'(mask)) -> bf16 planes / fp32.  One thread per 8 consecutive columns.
+struct FinishP {
+  const float* ws; int ksplit; long long slab, rows; int n_pad, n_valid;
+  const float* bias; int bias_mod, act;
+  const bf16* mask; long long mask_ps; int mask_act;
+  char* out; long long out_ps; int out_kind, out_ld, planes;
+};
+
+__global__ void __launch_bounds__(256) sg_splitk_finish_kernel(const FinishP p) {
+  const int groups = p.n_pad >> 3;
+  const long long total = p.rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / groups;
+    const int n0 = (int)(i - row * groups) * 8;
+    if (n0 >= p.n_valid) continue;
+    float v[8];
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.ws + row * p.n_pad + n0);
+      float4 a = __ldcs(src), b = __ldcs(src + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    for (int s = 1; s < p.ksplit; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(p.ws + (long long)s * p.slab + row * p.n_pad + n0);
+      float4 a = __ldcs(src), b = __ldcs(src + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    const int nv = min(8, p.n_valid - n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = v[j];
+      if (p.bias != nullptr && j < nv) { const int n = n0 + j; x += __ldg(p.bias + (p.bias_mod > 0 ? n % p.bias_mod : n)); }
+      v[j] = apply_act(x, p.act);
+    }
+    const long long eoff = row * p.out_ld + n0;
+    if (p.mask != nullptr) {
+      for (int j = 0; j < nv; ++j) v[j] *= act_grad_from_output(__bfloat162float(p.mask[eoff + j]), p.mask_act);
+    }
+    if (p.out_kind == SG_OUT_BF16) {
+      bf16* o = reinterpret_cast<bf16*>(p.out) + eoff;
+      if (nv == 8 && (p.out_ld & 7) == 0) {
+        uint4 hi;
+        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]); hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(o) = hi;
+        if (p.planes == 2) {
+          uint4 lo;
+          lo.x = pack_bf16x2(v[0] - bf16lo_to_f(hi.x), v[1] - bf16hi_to_f(hi.x));
+          lo.y = pack_bf16x2(v[2] - bf16lo_to_f(hi.y), v[3] - bf16hi_to_f(hi.y));
+          lo.z = pack_bf16x2(v[4] - bf16lo_to_f(hi.z), v[5] - bf16hi_to_f(hi.z));
+          lo.w = pack_bf16x2(v[6] - bf16lo_to_f(hi.w), v[7] - bf16hi_to_f(hi.w));
+          *reinterpret_cast<uint4*>(o + p.out_ps) = lo;
+        }
+      } else {
+        for (int j = 0; j < nv; ++j) {
+          const bf16 h = __float2bfloat16_rn(v[j]);
+          o[j] = h;
+          if (p.planes == 2) o[p.out_ps + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+        }
+      }
+    } else {
+      float* o = reinterpret_cast<float*>(p.out) + eoff;
+      for (int j = 0; j < nv; ++j) o[j] = v[j];
+    }
+  }
+}
+
+// Tile configuration shared by sg_igemm and sg_igemm_plan.  `ws_ok`: a split-K workspace may be used.
+// Split-K (fp32 partial slabs + sg_splitk_finish_kernel) is chosen when the output has too few tiles to fill the machine even at
+// the widest N tile and K is long: Conv3d(128->256) on 8^3 -> 4^3 at B=64 is 32 row tiles x K = 8192; narrowing N to 64 (the
+// alternative) fills 128 SMs with 128x64 MMAs that run at a third of the tensor rate (A-operand shared-memory reads per MMA).
+struct TileCfg { int bn, mt, ksplit; size_t ws_bytes; long long out_rows; };
+
+static int igemm_tiles(const sg_igemm_args* a, bool ws_ok, TileCfg* t) {
+  const int sms = sg_num_sms();
+  const long long row_tiles = (a->rows + 127) / 128;
+  const int classes = (a->mode == SG_MODE_CONVT) ? 8 : 1;
+  const int kchunks = a->k / 64;
+  int bn = a->bn, mt = a->mt, ksplit = a->ksplit;
+  t->out_rows = a->rows * classes;
+  t->ws_bytes = 0;
+  bool auto_split = false;
+  if (bn <= 0) {
+    bn = a->n_pad;
+    if (bn > 256) {                       // largest divisor of n_pad that is a multiple of 16 and <= 256
+      bn = 256;
+      while (a->n_pad % bn) bn -= 16;
+    }
+    const long long items = row_tiles * classes * (a->n_pad / bn);
+    const char* nsk = getenv("SG_B200_NO_SPLITK");
+    const bool no_split = nsk && nsk[0] == '1';
+    if (ksplit <= 0 && ws_ok && !no_split && a->out_kind != SG_OUT_F32_ATOMIC && items * 2 <= sms && kchunks >= 32 && (bn & 31) == 0) {
+      int ks = (int)(sms / items);
+      while (ks > 1 && kchunks / ks < 16) --ks;
+      if (ks > 1) { ksplit = ks; auto_split = true; }
+    }
+    // not enough work for the machine: narrow the N tile (keeps tensor throughput, multiplies CTAs)
+    if (!auto_split)
+      while (bn > 64 && (bn % 32) == 0 && row_tiles * classes * (a->n_pad / bn) < sms) bn /= 2;
+  }
+  if (bn > 256 || (bn & 15) || a->n_pad % bn) return sg_fail(-20, "sg_igemm: bad bn");
+  const int n_tiles = a->n_pad / bn;
+  // two M sub-tiles share every B tile (halves the weight traffic out of L2) once there is more than one wave of work
+  // (not when that would cost the accumulator double buffer: with bn = 256 two sub-tiles fill TMEM and the epilogue serialises)
+  if (mt <= 0) mt = (row_tiles * classes * n_tiles > sms && bn * 4 <= 512) ? 2 : 1;
+  if (mt < 1 || mt > 2 || mt * bn > 512) return sg_fail(-21, "sg_igemm: bad mt");
+  if (ksplit <= 0) ksplit = 1;
+  if (ksplit > kchunks) ksplit = kchunks;
+  {  // no empty split
+    int cps = (kchunks + ksplit - 1) / ksplit;
+    ksplit = (kchunks + cps - 1) / cps;
+  }
+  if (ksplit > 1 && a->out_kind != SG_OUT_F32_ATOMIC) {
+    if (!ws_ok) {
+      if (auto_split) ksplit = 1; else return sg_fail(-22, "sg_igemm: split-K needs SG_OUT_F32_ATOMIC or a splitk_ws workspace (sg_igemm_plan)");
+    } else {
+      t->ws_bytes = (size_t)ksplit * (size_t)t->out_rows * (size_t)a->n_pad * sizeof(float);
+    }
+  }
+  t->bn = bn; t->mt = mt; t->ksplit = ksplit;
+  return 0;
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -831,29 +955,20 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   const int sms = sg_num_sms();
   const long long row_tiles = (a->rows + 127) / 128;
   // ---- tile configuration
-  int bn = a->bn, mt = a->mt, ksplit = a->ksplit;
-  if (bn <= 0) {
-    bn = a->n_pad;
-    if (bn > 256) {                       // largest divisor of n_pad that is a multiple of 16 and <= 256
-      bn = 256;
-      while (a->n_pad % bn) bn -= 16;
+  TileCfg tc;
+  {
+    const bool ws_ok = a->splitk_ws != nullptr;
+    rc = igemm_tiles(a, ws_ok, &tc);
+    if (rc) return rc;
+    if (tc.ws_bytes > (size_t)a->splitk_ws_bytes) {
+      if (a->ksplit > 1) return sg_fail(-22, "sg_igemm: splitk_ws too small (see sg_igemm_plan)");
+      rc = igemm_tiles(a, false, &tc);            // auto split without room: fall back to the unsplit configuration
+      if (rc) return rc;
     }
-    // not enough work for the machine: narrow the N tile (keeps tensor throughput, multiplies CTAs)
-    while (bn > 64 && (bn % 32) == 0 && row_tiles * p.classes * (a->n_pad / bn) < sms) bn /= 2;
   }
-  if (bn > 256 || (bn & 15) || a->n_pad % bn) return sg_fail(-20, "sg_igemm: bad bn");
+  int bn = tc.bn, mt = tc.mt, ksplit = tc.ksplit;
   const int n_tiles = a->n_pad / bn;
-  // two M sub-tiles share every B tile (halves the weight traffic out of L2) once there is more than one wave of work
-  // (not when that would cost the accumulator double buffer: with bn = 256 two sub-tiles fill TMEM and the epilogue serialises)
-  if (mt <= 0) mt = (row_tiles * p.classes * n_tiles > sms && bn * 4 <= 512) ? 2 : 1;
-  if (mt < 1 || mt > 2 || mt * bn > 512) return sg_fail(-21, "sg_igemm: bad mt");
-  if (ksplit <= 0) ksplit = 1;
-  if (ksplit > p.kchunks) ksplit = p.kchunks;
-  if (ksplit > 1 && a->out_kind != SG_OUT_F32_ATOMIC) return sg_fail(-22, "sg_igemm: split-K needs SG_OUT_F32_ATOMIC");
-  {  // no empty split
-    int cps = (p.kchunks + ksplit - 1) / ksplit;
-    ksplit = (p.kchunks + cps - 1) / cps;
-  }
+  const bool split_ws = ksplit > 1 && a->out_kind != SG_OUT_F32_ATOMIC;
   // explicit/auto mt=2 that would leave fewer than 2 pipeline stages falls back to one M sub-tile
   if (mt == 2) {
     unsigned sb = ((unsigned)(2 * a->planes * kTileBytes + a->planes * bn * 128) + 1023u) & ~1023u;
@@ -861,6 +976,12 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     if ((227u * 1024u - kSmemHeader - kt) / sb < 2) mt = 1;
   }
   p.bn = bn; p.mt = mt; p.ksplit = ksplit;
+  if (split_ws) {
+    // K splits write fp32 partial slabs [ks][out rows][n_pad]; bias / activation / mask / bf16 conversion happen in the finish kernel
+    p.out = (char*)a->splitk_ws; p.out_ps = 0; p.out_kind = SG_OUT_F32; p.out_ld = a->n_pad;
+    p.ks_stride = tc.out_rows * (long long)a->n_pad;
+    p.bias = nullptr; p.bias_mod = 0; p.act = ACT_NONE; p.mask = nullptr;
+  }
   p.n_tiles = n_tiles;
   p.m_tiles = (int)((row_tiles + mt - 1) / mt);
   p.work_total = (long long)p.classes * n_tiles * p.m_tiles * ksplit;
@@ -966,6 +1087,33 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
   sg_count_launch();
+  if (split_ws) {
+    FinishP f;
+    f.ws = (const float*)a->splitk_ws; f.ksplit = ksplit; f.slab = p.ks_stride; f.rows = tc.out_rows; f.n_pad = a->n_pad; f.n_valid = a->n_valid;
+    f.bias = a->bias; f.bias_mod = a->bias_mod; f.act = a->act;
+    f.mask = (const bf16*)a->mask; f.mask_ps = a->mask_plane_stride; f.mask_act = a->mask_act;
+    f.out = (char*)a->out; f.out_ps = a->out_plane_stride; f.out_kind = a->out_kind; f.out_ld = a->out_ld; f.planes = a->planes;
+    const long long total = tc.out_rows * (a->n_pad >> 3);
+    const int fgrid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
+    sg_splitk_finish_kernel<<<fgrid, 256, 0, (cudaStream_t)stream>>>(f);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+    sg_count_launch();
+  }
+  return 0;
+}
+
+// Workspace (bytes of fp32 partial slabs) sg_igemm would use for these arguments when `splitk_ws` is provided; 0 = no split-K.
+extern "C" int sg_igemm_plan(const sg_igemm_args* a, size_t* ws_bytes) {
+  if (!ws_bytes) return sg_fail(-1, "sg_igemm_plan: null");
+  *ws_bytes = 0;
+  int rc = igemm_validate(a);
+  if (rc) return rc;
+  if (a->rows == 0) return 0;
+  TileCfg tc;
+  rc = igemm_tiles(a, true, &tc);
+  if (rc) return rc;
+  *ws_bytes = tc.ws_bytes;
   return 0;
 }
 

@@ -111,6 +111,9 @@ def pack_linear_dgrad(w, planes, n_pad=None):
 
 
 # ------------------------------------------------------------------------------------------------- implicit GEMM
+_SPLITK_MAX_ELEMS = 148 * 128 * 256          # split-K only pays when the output has fewer tiles than SMs: skip the plan call otherwise
+
+
 def igemm(mode, planes, a, a_dims, rows, k, b_img, n_valid, out, out_ld, out_kind=L.OUT_BF16, bias=None, act=L.ACT_NONE,
           a2=None, a2_c=0, mask=None, mask_act=L.ACT_NONE, out_dims=(0, 0, 0), bn=0, mt=0, ksplit=0, n_pad=None, bias_mod=0):
     _require_cuda(a, b_img, out)
@@ -134,6 +137,13 @@ def igemm(mode, planes, a, a_dims, rows, k, b_img, n_valid, out, out_ld, out_kin
     args.out_plane_stride = out.stride(0) if (out.dtype == torch.bfloat16 and out.shape[0] == 2) else 0
     args.out_kind, args.out_ld = out_kind, out_ld
     args.out_d, args.out_h, args.out_w = out_dims
+    if out_kind != L.OUT_F32_ATOMIC and rows * (8 if mode == L.MODE_CONVT else 1) * n_pad <= _SPLITK_MAX_ELEMS:
+        # few output tiles x long K (e.g. Conv3d(128->256) 8^3 -> 4^3): the library may split K over fp32 partial slabs
+        nbytes = ctypes.c_size_t(0)
+        L.check(L.lib().sg_igemm_plan(ctypes.byref(args), ctypes.byref(nbytes)), 'sg_igemm_plan')
+        if nbytes.value:
+            ws = torch.empty(nbytes.value // 4, dtype=torch.float32, device=out.device)
+            args.splitk_ws, args.splitk_ws_bytes = ctypes.c_void_p(ws.data_ptr()), nbytes.value
     L.check(L.lib().sg_igemm(ctypes.byref(args), stream()), 'sg_igemm')
     return out
 

@@ -238,3 +238,36 @@ def test_wgrad(planes, merge_n):
     F.conv3d(q(vol, planes).unsqueeze(1), wref, None, stride=2, padding=1).backward(q(dy, planes).permute(0, 4, 1, 2, 3))
     report('wgrad-patch p%d m%d' % (planes, merge_n), g, wref.grad, TOL_F32)
     check_error_word()
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+@pytest.mark.parametrize('mode,b,r,cin,cout,ks', [('conv', 8, 8, 128, 256, 0), ('conv', 5, 8, 128, 256, 3), ('convt', 3, 4, 256, 128, 2),
+                                                   ('conv', 2, 8, 64, 40, 4)])
+def test_splitk_partial_slabs(mode, b, r, cin, cout, ks, planes, monkeypatch):
+    """Split-K through fp32 partial slabs + the finish kernel (bias, LeakyReLU, mask, bf16 hi/lo planes) against the same layer with
+    SG_B200_NO_SPLITK=1: the shape class of Conv3d(128->256) 8^3 -> 4^3 (few output tiles x K = 8192).  ks = 0 is the auto policy."""
+    L, raw = _imports()
+    x = raw.to_planes(rnd((b, r, r, r, cin), 1), planes)
+    bias = rnd((cout,), 3)
+    if mode == 'conv':
+        w = rnd((cout, cin, 4, 4, 4), 2, 0.05)
+        img, gmode, k, rows, ro = raw.pack_conv_fwd(w, planes), L.MODE_CONV, 64 * cin, b * (r // 2) ** 3, r // 2
+        out_rows, od = rows, (0, 0, 0)
+    else:
+        w = rnd((cin, cout, 4, 4, 4), 2, 0.05)
+        img, gmode, k, rows, ro = raw.pack_convt_fwd(w, planes), L.MODE_CONVT, 8 * cin, b * r ** 3, 2 * r
+        out_rows, od = b * ro ** 3, (ro, ro, ro)
+    mask = raw.to_planes(rnd((out_rows, cout), 4), planes)
+    outs = []
+    for split in (True, False):
+        if not split:
+            monkeypatch.setenv('SG_B200_NO_SPLITK', '1')
+        y = torch.zeros((planes, out_rows, cout), dtype=torch.bfloat16, device='cuda')
+        launches0 = L.lib().sg_launch_count()
+        raw.igemm(gmode, planes, x, (b, r, r, r, cin), rows, k, img, cout, y, cout, bias=bias, act=L.ACT_LRELU, mask=mask,
+                  mask_act=L.ACT_LRELU, out_dims=od, ksplit=ks if split else 0)
+        outs.append((raw.from_planes(y), L.lib().sg_launch_count() - launches0))
+    monkeypatch.delenv('SG_B200_NO_SPLITK')
+    assert outs[0][1] == 2 and outs[1][1] == 1, 'expected main + finish kernel vs a single launch, got %s' % ([o[1] for o in outs],)
+    report('splitk %s p%d ks%d' % (mode, planes, ks), outs[0][0], outs[1][0], 4e-3 if planes == 1 else 2e-5)
+    check_error_word()
