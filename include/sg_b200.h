@@ -204,6 +204,38 @@ typedef struct {
 int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream);
 int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32_t* aux_floats);
 
+/* Single-latent inference with the same fused kernel (SDFNet.evaluate_in_batches / get_voxels / get_normals, model/sdf_net.py:63-128, and
+ * the sphere tracer's step, rendering/raymarching.py:48-61,106-120): one latent code z for every point, so the latent part of layers1.0 and
+ * layers2.0 is the constant vector W[:, latent] z -- the host folds it into those layers' bias slots of `aux`, and the kernel streams no
+ * latent chunks at all (layers1.0 needs no MMA: it is entirely the fp32 accumulator pre-load).  0.79 of the forward FLOPs per point.
+ * Point source, one of: points[slot][3]; grid_r > 0: slot s is cell (s / r^2, s / r % r, s % r) of the util.get_voxel_coordinates grid and
+ * its coordinates come from grid_axis[3][r] (the float32(float64 linspace) values, bit-exact); trace_points (a tracing step).
+ * ray_index (optional) maps compact row i to its slot: rows outside the 1.1 sphere are simply not listed and the result lands in
+ * out[slot] of a pre-filled grid (model/sdf_net.py:7-19,77-95).  n_ptr (optional) is a device-resident row count <= n.
+ * Tracing step: p = trace_points[slot]; d = clamp(sdf(p) + sdf_offset, +-trace_clamp); p += trace_dirs[slot] * d (in place);
+ * hit = 0 < d < trace_threshold -> trace_hit[slot] = 1; miss = |p| > trace_radius (or p.y > trace_radius when trace_miss_y);
+ * every other ray is appended to next_index[atomicAdd(next_count, 1)].  out (optional) receives d. */
+typedef struct {
+  const float* points;
+  int64_t n;
+  const int32_t* n_ptr;
+  const int32_t* ray_index;
+  int32_t grid_r;
+  const float* grid_axis;
+  const void* w_img; /* the forward image of sg_sdfnet_fwd (its latent chunks are skipped) */
+  const float* aux;  /* sg_sdfnet_fwd's aux block with b + W[:, latent] z in the bias slots of layers1.0 / layers2.0 */
+  float* out;
+  void* mask_stash;  /* optional uint32 [7][n][8] ReLU masks (compact row order) for sg_sdfnet_bwd's xyz gradient */
+  float* trace_points;
+  const float* trace_dirs;
+  uint8_t* trace_hit;
+  int32_t* next_index;
+  int32_t* next_count;
+  float sdf_offset, trace_clamp, trace_threshold, trace_radius;
+  int32_t trace_miss_y;
+} sg_sdfnet_infer_args;
+int sg_sdfnet_infer(const sg_sdfnet_infer_args* a, void* stream);
+
 /* Fused input-gradient chain of the same MLP (what autograd runs for SDFNet.forward, model/sdf_net.py:56-61, between the
  * tanh head and layers1.0): g7 = gout*(1-out^2)*w8*[h7>0], then g_{l-1} = (g_l . W_l[:, :256]) * [h_{l-1}>0] for l = 7..2,
  * one persistent CTA per tile pair.  mask_stash = the forward's 1-bit ReLU masks; wt_img = 24 chunks of 32 KB = sg_pack_b images of the
@@ -219,9 +251,19 @@ typedef struct {
   const void* wt_img;
   const float* w8;
   int64_t n;
-  void* gstash;
+  void* gstash;        /* may be NULL when only gpoints is wanted (SDFNet.get_normals: nothing but [n][3] floats leaves the SM) */
+  float* gpoints;      /* optional [n][3]: gradient w.r.t. the point coordinates, accumulated inside the drains of g_5 and g_1 */
+  const float* xyz_w;  /* with gpoints: fp32 [2][3][256] = layers1.0.weight[:, 0:3]^T, layers2.0.weight[:, 256:259]^T */
 } sg_sdfnet_bwd_args;
 int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream);
+
+/* ---- SDFNet inference consumers / voxel data path ---- */
+/* Cells s = (ix*r + iy)*r + iz of the util.get_voxel_coordinates(r) grid (util.py:60-74) with |p| < radius, the sphere mask of
+ * SDFVoxelizationHelperData (model/sdf_net.py:12-14), evaluated in numpy's float32 arithmetic operation by operation (bit-exact set).
+ * axis = [3][r] coordinate tables; index_out has room for r^3 entries (unordered); *count must be zero on entry. */
+int sg_grid_sphere_index(int r, const float* axis, float radius, int32_t* index_out, int32_t* count, void* stream);
+/* VoxelDataset.__getitem__ (datasets.py:16-23) on a whole raw batch: dst = clamp(src, -clamp, clamp) [/ clamp], float32, bit-exact */
+int sg_voxel_ingest(const float* src, float* dst, int64_t n, float clamp, int rescale, void* stream);
 
 /* ---- misc ---- */
 int sg_abi_version(void);

@@ -52,7 +52,15 @@ class SgSdfnetFwdArgs(ctypes.Structure):
 
 class SgSdfnetBwdArgs(ctypes.Structure):
     _fields_ = [('gout', c_void_p), ('out', c_void_p), ('mask_stash', c_void_p), ('wt_img', c_void_p), ('w8', c_void_p),
-                ('n', c_int64), ('gstash', c_void_p)]
+                ('n', c_int64), ('gstash', c_void_p), ('gpoints', c_void_p), ('xyz_w', c_void_p)]
+
+
+class SgSdfnetInferArgs(ctypes.Structure):
+    _fields_ = [('points', c_void_p), ('n', c_int64), ('n_ptr', c_void_p), ('ray_index', c_void_p), ('grid_r', c_int32),
+                ('grid_axis', c_void_p), ('w_img', c_void_p), ('aux', c_void_p), ('out', c_void_p), ('mask_stash', c_void_p),
+                ('trace_points', c_void_p), ('trace_dirs', c_void_p), ('trace_hit', c_void_p), ('next_index', c_void_p),
+                ('next_count', c_void_p), ('sdf_offset', c_float), ('trace_clamp', c_float), ('trace_threshold', c_float),
+                ('trace_radius', c_float), ('trace_miss_y', c_int32)]
 
 
 # every symbol include/sg_b200.h declares, with (restype, argtypes); tests check that all of them resolve
@@ -75,6 +83,7 @@ SYMBOLS = {
     'sg_sdfnet_fwd': (c_int32, [ctypes.POINTER(SgSdfnetFwdArgs), c_void_p]),
     'sg_sdfnet_fwd_layout': (c_int32, [ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
     'sg_sdfnet_bwd': (c_int32, [ctypes.POINTER(SgSdfnetBwdArgs), c_void_p]),
+    'sg_sdfnet_infer': (c_int32, [ctypes.POINTER(SgSdfnetInferArgs), c_void_p]),
     # p = pointer, l = int64, i = int32, f = float (see _sig)
     'sg_act_bwd': 'plplpliliipp',
     'sg_bn_stats': 'plilipp',
@@ -100,6 +109,8 @@ SYMBOLS = {
     'sg_clamp': 'plffp',
     'sg_sum_f32': 'plpp',
     'sg_l1_loss_grad': 'ppplpp',
+    'sg_grid_sphere_index': 'ipfppp',
+    'sg_voxel_ingest': 'pplfip',
 }
 
 _SIG = {'p': c_void_p, 'l': c_int64, 'i': c_int32, 'f': c_float}

@@ -59,6 +59,15 @@ struct SdfP {
   int* err;
   int tma_stash;            // stash rows of layers 1..6 leave through TMA tile stores out of the activation tiles in SMEM
   CUtensorMap tm_stash;     // bf16 [7][n][256], box [1][128][64], 128B swizzle
+  // ---- single-latent inference (kernel instantiation FOLDED = true): the latent part of layers1.0 / layers2.0 is the constant
+  // vector W[:, latent] z, folded into the bias columns of the aux block by the host, so those layers stream no latent chunks
+  const int* ray_index;     // compact row -> slot of the point / output arrays (NULL: identity)
+  const int* n_ptr;         // device-resident row count (NULL: n) -- sphere tracing compacts its ray list on the device
+  int grid_r;               // > 0: slot s is grid cell (s / r^2, s / r % r, s % r); coordinates come from grid_axis[3][r]
+  const float* grid_axis;
+  // sphere-tracing step (rendering/raymarching.py:106-120 and :48-61): points advance in place, survivors are re-listed
+  float* trace_points; const float* trace_dirs; unsigned char* trace_hit; int* next_index; int* next_count;
+  float sdf_offset, trace_clamp, trace_threshold, trace_radius; int trace_miss_y;
 };
 
 // aux layout (floats)
@@ -103,10 +112,35 @@ __device__ __forceinline__ void sdf_acc_init(int l, int col, float px, float py,
   }
 }
 
+// where the point of compact row `gr` lives / where its result goes
+template <bool FOLDED>
+__device__ __forceinline__ long long sdf_slot(const SdfP& p, long long gr) {
+  if (FOLDED && p.ray_index != nullptr) return (long long)__ldg(p.ray_index + gr);
+  return gr;
+}
+template <bool FOLDED>
+__device__ __forceinline__ void sdf_load_point(const SdfP& p, long long slot, float& x, float& y, float& z) {
+  if (FOLDED && p.grid_r > 0) {
+    const uint32_t s = (uint32_t)slot, r = (uint32_t)p.grid_r;
+    const uint32_t iz = s % r, t = s / r, iy = t % r, ix = t / r;
+    x = __ldg(p.grid_axis + ix); y = __ldg(p.grid_axis + r + iy); z = __ldg(p.grid_axis + 2 * r + iz);
+    return;
+  }
+  if (FOLDED && p.trace_points != nullptr) {      // advanced in place by this very kernel (other rays): plain loads, not the read-only path
+    const float* src = p.trace_points + slot * 3;
+    x = src[0]; y = src[1]; z = src[2];
+    return;
+  }
+  x = __ldg(p.points + slot * 3); y = __ldg(p.points + slot * 3 + 1); z = __ldg(p.points + slot * 3 + 2);
+}
+
+template <bool FOLDED>
 __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __grid_constant__ SdfP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SdfHdr* hdr = reinterpret_cast<SdfHdr*>(smem);
   const int tid = threadIdx.x, lane = tid & 31;
+  const long long n_rows = (FOLDED && p.n_ptr != nullptr) ? (long long)__ldg(p.n_ptr) : p.n;
+  const long long n_pairs = (FOLDED && p.n_ptr != nullptr) ? ((n_rows + kTileRows - 1) / kTileRows + 1) / 2 : p.pairs;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // broadcast: the compiler can keep everything derived from it uniform
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -130,10 +164,11 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
   if (warp == 0) {
     // ================================================================ weight loader
     uint32_t g = 0;
-    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
-      for (int j = 0; j < kSdfStreamChunks; ++j, ++g) {
+    for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+      for (int j = 0; j < (FOLDED ? 24 : kSdfStreamChunks); ++j, ++g) {
         // stream position -> image chunk: [14,16) and [20,22) are the latent chunks 18,19 of layers2.0, [16,20) its hidden chunks 14-17
-        const int ic = j < 14 ? j : (j < 16 ? j + 4 : j - 2);
+        // folded latent: only the hidden chunks 2..17 and 20..27
+        const int ic = FOLDED ? (j < 16 ? j + 2 : j + 4) : (j < 14 ? j : (j < 16 ? j + 4 : j - 2));
         const uint32_t st = g & 1u;
         mbar_wait(&hdr->w_empty[st], ((g >> 1) & 1u) ^ 1u, p.err);
         if (elect_one()) {
@@ -173,7 +208,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
       __syncwarp();
       g += 2;
     };
-    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+    for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
       for (int l = 1; l <= 7; ++l) {
         // h[t] holds the activations of layer l-1 and accumulator t is drained and re-initialised
         for (int t = 0; t < 2; ++t) { mbar_wait(&hdr->h_ready[t], hr_n[t] & 1u, p.err); ++hr_n[t]; }
@@ -185,13 +220,18 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
           tma_store_commit();
         }
         if (l == 1) {
+          if (FOLDED) {       // layers1.0 is entirely in the accumulator pre-load (xyz columns + bias + W[:, latent] z): no MMA
+            if (elect_one()) { umma_commit(&hdr->acc_full[0]); umma_commit(&hdr->acc_full[1]); }
+            __syncwarp();
+            continue;
+          }
           wait_two_chunks();
           latent_mma(0, true);
           latent_mma(1, true);
           release_two_chunks();
           continue;
         }
-        if (l == 5) {   // latent part of layers2.0 for tile A first: tile B's latent rows are gathered under the hidden chunks
+        if (l == 5 && !FOLDED) {   // latent part of layers2.0 for tile A first: tile B's latent rows are gathered under the hidden chunks
           wait_two_chunks();
           latent_mma(0, false);
           release_two_chunks();
@@ -207,13 +247,13 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a + kk * 32, 16, 1024), umma_desc(b + kk * 32, 16, 1024), idesc, 1u);
               if (c == 3 && t == 0 && p.tma_stash) tma_store_wait_read();   // the epilogue overwrites the tiles after acc_full
-              if (c == 3 && (l != 5 || t == 0)) umma_commit(&hdr->acc_full[t]);
+              if (c == 3 && (FOLDED || l != 5 || t == 0)) umma_commit(&hdr->acc_full[t]);
             }
             umma_commit(&hdr->w_empty[g & 1u]);
           }
           __syncwarp();
         }
-        if (l == 5) {
+        if (l == 5 && !FOLDED) {
           wait_two_chunks();
           latent_mma(1, true);
           release_two_chunks();
@@ -225,7 +265,8 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
     // ================================================================ latent gather: fp32 table rows -> bf16 swizzled A tile
     const int gw = warp - 2;
     uint32_t use = 0;
-    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+    if (!FOLDED)
+    for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
       for (int u = 0; u < 4; ++u, ++use) {          // (A,L1) (B,L1) (A,L5) (B,L5)
         const long long tile = pr * 2 + (u & 1);
         if (use > 0) mbar_wait(&hdr->lat_empty, (use - 1) & 1u, p.err);
@@ -233,7 +274,7 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         // table row of each of this warp's 32 points: one coalesced index load, broadcast by shuffle (no dependent load chain)
         const long long gr_l = tile * kTileRows + gw * 32 + lane;
         long long my_row = -1;
-        if (gr_l < p.n) my_row = p.index ? (long long)__ldg(p.index + gr_l) : gr_l;
+        if (gr_l < n_rows) my_row = p.index ? (long long)__ldg(p.index + gr_l) : gr_l;
 #pragma unroll 16
         for (int i = 0; i < 32; ++i) {
           const int r = gw * 32 + i;
@@ -260,9 +301,10 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cbase);
     uint32_t af_n = 0;
     float px = 0.f, py = 0.f, pz = 0.f;
+    long long cur_slot = 0;
     {
       const long long gr = ((long long)blockIdx.x * 2 + t) * kTileRows + r;
-      if (gr < p.n) { px = __ldg(p.points + gr * 3); py = __ldg(p.points + gr * 3 + 1); pz = __ldg(p.points + gr * 3 + 2); }
+      if (gr < n_rows) { cur_slot = sdf_slot<FOLDED>(p, gr); sdf_load_point<FOLDED>(p, cur_slot, px, py, pz); }
       // accumulator of layer 1 of the first pair
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -274,19 +316,20 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
       tc_fence_before();
       mbar_arrive(&hdr->h_ready[t]);
     }
-    for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
+    for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
       const long long gr = (pr * 2 + t) * kTileRows + r;
-      const bool valid = gr < p.n;
+      const bool valid = gr < n_rows;
       // points of this CTA's next pair (its layer-1 accumulator is initialised at the end of this pair)
       const long long npr = pr + gridDim.x;
       const long long ngr = (npr * 2 + t) * kTileRows + r;
       float nx = 0.f, ny = 0.f, nz = 0.f;
-      if (npr < p.pairs && ngr < p.n) { nx = __ldg(p.points + ngr * 3); ny = __ldg(p.points + ngr * 3 + 1); nz = __ldg(p.points + ngr * 3 + 2); }
+      long long next_slot = 0;
+      if (npr < n_pairs && ngr < n_rows) { next_slot = sdf_slot<FOLDED>(p, ngr); sdf_load_point<FOLDED>(p, next_slot, nx, ny, nz); }
       for (int l = 1; l <= 7; ++l) {
         mbar_wait(&hdr->acc_full[t], af_n & 1u, p.err); ++af_n;
         tc_fence_after();
         const int nl = (l < 7) ? l + 1 : 1;                        // layer whose accumulator start value goes in behind the drain
-        const bool init_next = (l < 7) || (npr < p.pairs);
+        const bool init_next = (l < 7) || (npr < n_pairs);
         const float ix = (l < 7) ? px : nx, iy = (l < 7) ? py : ny, iz = (l < 7) ? pz : nz;
         float dot = 0.f;
         bf16* srow = (p.stash != nullptr && valid && (l == 7 || !p.tma_stash)) ? p.stash + ((size_t)(l - 1) * (size_t)p.n + (size_t)gr) * 256 + cbase : nullptr;
@@ -340,14 +383,31 @@ __global__ void __launch_bounds__(kSdfThreads, 1) sg_sdfnet_fwd_kernel(const __g
         if (l == 7) {       // the two column halves of a row meet through shared memory (named barrier of the tile's 8 warps)
           if (half == 1) dotbuf[r] = dot;
           asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
-          if (half == 0 && valid) p.out[gr] = tanhf(dot + dotbuf[r] + c_sdf_aux[kAuxB8]);
+          if (half == 0 && valid) {
+            const float sdf = tanhf(dot + dotbuf[r] + c_sdf_aux[kAuxB8]);
+            if (FOLDED && p.trace_points != nullptr) {
+              // one sphere-tracing step of ray `cur_slot` (rendering/raymarching.py:108-118): advance by the clamped distance, classify
+              const float d = fminf(fmaxf(sdf + p.sdf_offset, -p.trace_clamp), p.trace_clamp);
+              const float* dir = p.trace_dirs + cur_slot * 3;
+              const float qx = px + __ldg(dir) * d, qy = py + __ldg(dir + 1) * d, qz = pz + __ldg(dir + 2) * d;
+              float* dst = p.trace_points + cur_slot * 3;
+              dst[0] = qx; dst[1] = qy; dst[2] = qz;
+              const bool hit = d > 0.f && d < p.trace_threshold;
+              const bool miss = p.trace_miss_y ? (qy > p.trace_radius) : (sqrtf(qx * qx + qy * qy + qz * qz) > p.trace_radius);
+              if (hit) p.trace_hit[cur_slot] = 1;
+              else if (!miss) p.next_index[atomicAdd(p.next_count, 1)] = (int)cur_slot;
+              if (p.out != nullptr) p.out[cur_slot] = d;
+            } else {
+              p.out[FOLDED ? cur_slot : gr] = sdf;
+            }
+          }
         }
         tmem_st_wait();
         if (l < 7) fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
         tc_fence_before();
         mbar_arrive(&hdr->h_ready[t]);
       }
-      px = nx; py = ny; pz = nz;
+      px = nx; py = ny; pz = nz; cur_slot = next_slot;
     }
   }
   tc_fence_before();
@@ -368,8 +428,14 @@ struct SdfBwdP {
   int* err;
   int tma_stash;            // g_7..g_2 leave through TMA tile stores out of the operand tiles in SMEM
   CUtensorMap tm_stash;     // bf16 [7][n][256], box [1][128][64], 128B swizzle
+  float* gpoints;           // XYZ instantiation: d out / d xyz per point [n][3] = g_1 W1[:, 0:3] + g_5 W5[:, 256:259] (model/sdf_net.py:57,59)
 };
 
+__constant__ float c_sdf_bwd_xyz[2 * 3 * 256];   // XYZ: [layers1.0 | layers2.0][x, y, z][256 out-features]
+
+// XYZ = true: additionally accumulates the gradient w.r.t. the point coordinates inside the drains of g_5 and g_1 (SDFNet.get_normals,
+// model/sdf_net.py:118-128) -- no K = 131 GEMMs, and with gstash == NULL nothing but [n][3] floats leaves the SM.
+template <bool XYZ>
 __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const __grid_constant__ SdfBwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SdfHdr* hdr = reinterpret_cast<SdfHdr*>(smem);
@@ -457,6 +523,9 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
       return __ldg(reinterpret_cast<const uint4*>(p.mstash + ((size_t)(6 - sidx) * (size_t)p.n + (size_t)g) * 8 + half * 4));
     };
     uint32_t af_n = 0;
+    float gxyz[3] = {0.f, 0.f, 0.f};
+    float* xyzbuf = reinterpret_cast<float*>(hbuf);     // [128 rows][3], column half 1 -> column half 0: this tile's operand region is idle
+                                                        // between the MMAs of layer 2 (acc_full) and the head of the CTA's next pair
     uint4 mcur = load_mask(blockIdx.x, 0);
     for (long long pr = blockIdx.x; pr < p.pairs; pr += gridDim.x) {
       const long long gr = (pr * 2 + t) * kTileRows + r;
@@ -487,7 +556,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
           const uint32_t chunk = (uint32_t)col >> 6, pbase = ((uint32_t)col & 63u) >> 3;
 #pragma unroll
           for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
-          if (valid && !p.tma_stash) { stg_256(grow + c * 32, pk[0], pk[1]); stg_256(grow + c * 32 + 16, pk[2], pk[3]); }
+          if (valid && !p.tma_stash && p.gstash != nullptr) { stg_256(grow + c * 32, pk[0], pk[1]); stg_256(grow + c * 32 + 16, pk[2], pk[3]); }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -509,6 +578,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
           tmem_ld_wait();
           const uint32_t bits = c == 0 ? mcur.x : (c == 1 ? mcur.y : (c == 2 ? mcur.z : mcur.w));
           uint4 pk[4];
+          const float* wxyz = c_sdf_bwd_xyz + (l == 6 ? 768 : 0) + col;     // XYZ: g_5 (drained at l = 6) meets layers2.0, g_1 (l = 2) layers1.0
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint32_t o[4];
@@ -518,6 +588,10 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
               const float lo = ((bits >> wd) & 1u) ? __uint_as_float(acc[2 * wd]) : 0.f;
               const float hi = ((bits >> (16 + wd)) & 1u) ? __uint_as_float(acc[2 * wd + 1]) : 0.f;
               o[k] = pack_bf16x2(lo, hi);
+              if (XYZ && (l == 6 || l == 2)) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) gxyz[d] = fmaf(hi, wxyz[d * 256 + 2 * wd + 1], fmaf(lo, wxyz[d * 256 + 2 * wd], gxyz[d]));
+              }
             }
             pk[u] = make_uint4(o[0], o[1], o[2], o[3]);
           }
@@ -526,7 +600,7 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
 #pragma unroll
             for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(hbuf + chunk * kTileBytes + sw128((uint32_t)r, pbase + u)) = pk[u];
           }
-          if (valid && (l == 2 || !p.tma_stash)) { stg_256(grow + c0, pk[0], pk[1]); stg_256(grow + c0 + 16, pk[2], pk[3]); }
+          if (valid && (l == 2 || !p.tma_stash) && p.gstash != nullptr) { stg_256(grow + c0, pk[0], pk[1]); stg_256(grow + c0 + 16, pk[2], pk[3]); }
         }
         if (l > 2) {
           fence_proxy_async();
@@ -534,6 +608,16 @@ __global__ void __launch_bounds__(kSdfBwdThreads, 1) sg_sdfnet_bwd_kernel(const 
           mbar_arrive(&hdr->h_ready[t]);
         } else {
           tc_fence_before();      // orders the accumulator reads before the head of the next pair arrives on h_ready
+          if (XYZ) {              // the two column halves of a row meet through shared memory (named barrier of the tile's 8 warps)
+            if (half == 1) { xyzbuf[r * 3] = gxyz[0]; xyzbuf[r * 3 + 1] = gxyz[1]; xyzbuf[r * 3 + 2] = gxyz[2]; }
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+            if (half == 0 && valid) {
+              float* dst = p.gpoints + gr * 3;
+              dst[0] = gxyz[0] + xyzbuf[r * 3]; dst[1] = gxyz[1] + xyzbuf[r * 3 + 1]; dst[2] = gxyz[2] + xyzbuf[r * 3 + 2];
+            }
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");      // xyzbuf is reused by this CTA's next pair
+            gxyz[0] = gxyz[1] = gxyz[2] = 0.f;
+          }
         }
         mcur = mnext;
       }
@@ -572,7 +656,7 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   p.tma_stash = (p.stash != nullptr && sdf_stash_map(&p.tm_stash, p.stash, a->n)) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
+    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -580,7 +664,44 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_aux, a->aux, sizeof(float) * kAuxFloats, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
   const int grid = (int)std::min<long long>(p.pairs, sg_num_sms());
-  sg_sdfnet_fwd_kernel<<<grid, kSdfThreads, kSdfSmem, (cudaStream_t)stream>>>(p);
+  sg_sdfnet_fwd_kernel<false><<<grid, kSdfThreads, kSdfSmem, (cudaStream_t)stream>>>(p);
+  SG_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+// Single-latent inference (evaluate_in_batches / get_voxels / get_normals / sphere tracing): see sg_b200.h
+extern "C" int sg_sdfnet_infer(const sg_sdfnet_infer_args* a, void* stream) {
+  if (!a || !a->w_img || !a->aux) return sg_fail(-1, "sg_sdfnet_infer: null weights");
+  const bool trace = a->trace_points != nullptr;
+  if (!trace && !a->out) return sg_fail(-1, "sg_sdfnet_infer: null out");
+  if (!trace && a->grid_r <= 0 && !a->points) return sg_fail(-1, "sg_sdfnet_infer: no point source (points, grid_r or trace_points)");
+  if (a->grid_r > 0 && (!a->grid_axis || a->grid_r > 1024)) return sg_fail(-2, "sg_sdfnet_infer: grid needs grid_axis[3][r], r <= 1024");
+  if (trace && (!a->trace_dirs || !a->trace_hit || !a->next_index || !a->next_count || !a->ray_index))
+    return sg_fail(-3, "sg_sdfnet_infer: a tracing step needs trace_dirs, trace_hit, ray_index, next_index, next_count");
+  if (a->n <= 0) return 0;
+  if (a->n >= (1LL << 31)) return sg_fail(-4, "sg_sdfnet_infer: n must be < 2^31");
+  SdfP p;
+  memset(&p, 0, sizeof(p));
+  p.points = a->points; p.n = a->n; p.n_ptr = a->n_ptr; p.ray_index = a->ray_index;
+  p.grid_r = a->grid_r; p.grid_axis = a->grid_axis;
+  p.w_img = (const char*)a->w_img; p.out = a->out; p.mstash = (uint32_t*)a->mask_stash;
+  p.trace_points = a->trace_points; p.trace_dirs = a->trace_dirs; p.trace_hit = a->trace_hit;
+  p.next_index = a->next_index; p.next_count = a->next_count;
+  p.sdf_offset = a->sdf_offset; p.trace_clamp = a->trace_clamp; p.trace_threshold = a->trace_threshold; p.trace_radius = a->trace_radius;
+  p.trace_miss_y = a->trace_miss_y;
+  const long long tiles = (a->n + kTileRows - 1) / kTileRows;
+  p.pairs = (tiles + 1) / 2;
+  p.err = sg_error_word();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
+    if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_aux, a->aux, sizeof(float) * kAuxFloats, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+  const int grid = (int)std::min<long long>(p.pairs, sg_num_sms());
+  sg_sdfnet_fwd_kernel<true><<<grid, kSdfThreads, kSdfSmem, (cudaStream_t)stream>>>(p);
   SG_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -593,7 +714,8 @@ extern "C" int sg_sdfnet_fwd_layout(int32_t* chunks, int32_t* chunk_bytes, int32
 }
 
 extern "C" int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream) {
-  if (!a || !a->gout || !a->out || !a->mask_stash || !a->wt_img || !a->w8 || !a->gstash) return sg_fail(-1, "sg_sdfnet_bwd: null");
+  if (!a || !a->gout || !a->out || !a->mask_stash || !a->wt_img || !a->w8 || (!a->gstash && !a->gpoints)) return sg_fail(-1, "sg_sdfnet_bwd: null");
+  if (a->gpoints && !a->xyz_w) return sg_fail(-1, "sg_sdfnet_bwd: gpoints needs xyz_w");
   if (a->n <= 0) return 0;
   SdfBwdP p;
   memset(&p, 0, sizeof(p));
@@ -602,17 +724,25 @@ extern "C" int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream) {
   const long long tiles = (a->n + kTileRows - 1) / kTileRows;
   p.pairs = (tiles + 1) / 2;
   p.err = sg_error_word();
-  p.tma_stash = sdf_stash_map(&p.tm_stash, p.gstash, a->n) ? 1 : 0;
+  p.gpoints = a->gpoints;
+  p.tma_stash = (p.gstash != nullptr && sdf_stash_map(&p.tm_stash, p.gstash, a->n)) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfBwdSmem);
+    cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfBwdSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sg_sdfnet_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfBwdSmem);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
   cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_w8, a->w8, sizeof(float) * 256, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
   const int grid = (int)std::min<long long>(p.pairs, sg_num_sms());
-  sg_sdfnet_bwd_kernel<<<grid, kSdfBwdThreads, kSdfBwdSmem, (cudaStream_t)stream>>>(p);
+  if (p.gpoints != nullptr) {
+    e = cudaMemcpyToSymbolAsync(c_sdf_bwd_xyz, a->xyz_w, sizeof(float) * 2 * 3 * 256, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+    sg_sdfnet_bwd_kernel<true><<<grid, kSdfBwdThreads, kSdfBwdSmem, (cudaStream_t)stream>>>(p);
+  } else {
+    sg_sdfnet_bwd_kernel<false><<<grid, kSdfBwdThreads, kSdfBwdSmem, (cudaStream_t)stream>>>(p);
+  }
   SG_CUDA_CHECK_LAUNCH();
   return 0;
 }

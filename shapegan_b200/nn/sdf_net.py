@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import raw
+from .. import raw, sdf_ops
 from ..sdf_ops import sdfnet_apply
 from . import LATENT_CODE_SIZE, SavableModule, _require_cuda
 
@@ -39,6 +39,27 @@ def get_points_in_unit_sphere(n, device):
     if x.shape[0] < n:
         print("Warning: Did not find enough points.")
     return x
+
+
+class _GridHelper:
+    """Device-side replacement of SDFVoxelizationHelperData for the fused voxelisation: axis tables [3, R] (the float32(float64
+    linspace) values of util.py:60-74) and the sorted list of cells with |p| < 1.1 (model/sdf_net.py:12), built on the device."""
+
+    def __init__(self, device, r, sphere_only):
+        axis = np.stack([np.linspace(-1, 1, r)] * 3).astype(np.float32)
+        self.axis = torch.tensor(axis, device=device)
+        self.index = raw.grid_sphere_index(r, self.axis, 1.1) if sphere_only else None
+        self.count = int(self.index.shape[0]) if sphere_only else r * r * r
+
+
+_grid_helpers = dict()
+
+
+def _grid_helper(device, r, sphere_only):
+    key = (str(device), r, sphere_only)
+    if key not in _grid_helpers:
+        _grid_helpers[key] = _GridHelper(device, r, sphere_only)
+    return _grid_helpers[key]
 
 
 class SDFVoxelizationHelperData():
@@ -105,19 +126,39 @@ class SDFNet(SavableModule):
 
     # ------------------------------------------------------------------ inference helpers (model/sdf_net.py:63-168)
     def evaluate_in_batches(self, points, latent_code, batch_size=100000, return_cpu_tensor=True):
-        """One latent code for all points; chunked like the reference (:63-75) but the latent is broadcast by index
-        instead of `.repeat(batch_size, 1)`."""
+        """One latent code for all points (:63-75).  bf16 mode: ONE launch of the folded single-latent kernel over all points (the
+        latent is a constant of the call: W[:, latent] z goes into the bias, see sdf_ops.folded_weights) instead of chunks of
+        `batch_size` with `.repeat(batch_size, 1)`; fp32x mode: chunked like the reference, latent broadcast by index."""
         n = points.shape[0]
-        table = latent_code.reshape(1, -1).to(points.device)
+        _require_cuda(points, 'SDFNet.evaluate_in_batches')
         with torch.no_grad():
-            result = torch.zeros((n,), device=points.device)
-            for start in range(0, n, batch_size):
-                chunk = points[start:start + batch_size, :]
-                zeros = torch.zeros((chunk.shape[0],), dtype=torch.int32, device=points.device)
-                result[start:start + batch_size] = self(chunk, table, zeros)
+            if n > 0 and sdf_ops.folded_enabled(self.latent_code_size):
+                result = torch.empty((n,), dtype=torch.float32, device=points.device)
+                sdf_ops.infer_single_latent(self._params(), latent_code.to(points.device), n=n, out=result, points=points.float().contiguous())
+            else:
+                table = latent_code.reshape(1, -1).to(points.device)
+                result = torch.zeros((n,), device=points.device)
+                for start in range(0, n, batch_size):
+                    chunk = points[start:start + batch_size, :]
+                    zeros = torch.zeros((chunk.shape[0],), dtype=torch.int32, device=points.device)
+                    result[start:start + batch_size] = self(chunk, table, zeros)
         return result.cpu() if return_cpu_tensor else result
 
     def get_voxels(self, latent_code, voxel_resolution, sphere_only=True, pad=True):
+        """:77-95.  bf16 mode: the grid never exists as a point list -- the kernel derives the coordinates of cell s from the axis
+        tables, only the cells inside the 1.1 sphere are listed (device-built index, cached per resolution) and every result is
+        scattered straight into the ones-filled grid."""
+        r = voxel_resolution
+        if sdf_ops.folded_enabled(self.latent_code_size):
+            helper = _grid_helper(self.device, r, sphere_only)
+            with torch.no_grad():
+                grid = torch.ones((r * r * r,), dtype=torch.float32, device=self.device)
+                sdf_ops.infer_single_latent(self._params(), latent_code.to(self.device), n=helper.count, out=grid, ray_index=helper.index,
+                                            grid_r=r, grid_axis=helper.axis)
+            voxels = grid.reshape(r, r, r).cpu().numpy()
+            if not sphere_only and pad:
+                voxels = np.pad(voxels, 1, mode='constant', constant_values=1)
+            return voxels
         key = (voxel_resolution, sphere_only)
         if key not in sdf_voxelization_helper:
             sdf_voxelization_helper[key] = SDFVoxelizationHelperData(self.device, voxel_resolution, sphere_only)
@@ -154,14 +195,27 @@ class SDFNet(SavableModule):
         mesh = self.get_mesh(latent_code, voxel_resolution=voxel_resolution, sphere_only=sphere_only, level=level)
         return mesh.sample(point_count)
 
-    def get_normals(self, latent_code, points):
-        if latent_code.requires_grad or points.requires_grad:
-            raise Exception('get_normals may only be called with tensors that don\'t require grad.')
+    def _sdf_and_gradient(self, latent_code, points):
+        """(sdf [n], d sdf / d xyz [n,3]) of one latent code; `points.grad` receives the gradient like the reference's backward()."""
+        if sdf_ops.folded_enabled(self.latent_code_size) and points.shape[0] > 0:
+            # analytic path: folded forward (ReLU masks only) + fused backward chain with the xyz gradient in its drains.  Unlike
+            # the reference's sdf.backward() (:122-126) this does NOT accumulate into the parameters' .grad -- nobody reads those.
+            with torch.no_grad():
+                sdf, g = sdf_ops.normals_single_latent(self._params(), latent_code.to(points.device), points.detach().float().contiguous(),
+                                                       normalize=False)
+            points.requires_grad = True
+            points.grad = g
+            return sdf, g
         points.requires_grad = True
         zeros = torch.zeros((points.shape[0],), dtype=torch.int32, device=points.device)
         sdf = self(points, latent_code.reshape(1, -1), zeros)
         sdf.backward(torch.ones(sdf.shape[0], device=self.device))
-        normals = points.grad
+        return sdf.detach(), points.grad
+
+    def get_normals(self, latent_code, points):
+        if latent_code.requires_grad or points.requires_grad:
+            raise Exception('get_normals may only be called with tensors that don\'t require grad.')
+        _, normals = self._sdf_and_gradient(latent_code, points)
         normals /= torch.norm(normals, dim=1).unsqueeze(dim=1)
         return normals
 
@@ -170,11 +224,7 @@ class SDFNet(SavableModule):
             points = get_points_in_unit_sphere(n=sample_size, device=self.device) * 1.1
         else:
             points = torch.rand((sample_size, 3), device=self.device) * 2.2 - 1
-        points.requires_grad = True
-        zeros = torch.zeros((points.shape[0],), dtype=torch.int32, device=points.device)
-        sdf = self(points, latent_code.reshape(1, -1), zeros)
-        sdf.backward(torch.ones((sdf.shape[0]), device=self.device))
-        normals = points.grad
+        sdf, normals = self._sdf_and_gradient(latent_code, points)
         normals /= torch.norm(normals, dim=1).unsqueeze(dim=1)
         points.requires_grad = False
         points -= normals * sdf.detach().unsqueeze(dim=1)        # project onto the surface along the normal

@@ -392,11 +392,42 @@ def sdfnet_fwd(points, latent, index, w_img, aux, stash=None, mask_stash=None):
     return out
 
 
-def sdfnet_bwd(gout, out, mask_stash, wt_img, w8):
+def sdfnet_bwd(gout, out, mask_stash, wt_img, w8, xyz_w=None, want_gstash=True):
     """Fused input-gradient chain (sg_sdfnet.cu): returns gstash bf16 [7, n, 256] = gradients w.r.t. the pre-activations
-    of layers 1..7."""
+    of layers 1..7 (None when want_gstash is False) and, with xyz_w [2,3,256], the gradient w.r.t. the points [n, 3]."""
     n = out.shape[0]
-    gstash = torch.empty((7, n, 256), dtype=torch.bfloat16, device=out.device)
-    a = L.SgSdfnetBwdArgs(_p(gout), _p(out), _p(mask_stash), _p(wt_img), _p(w8), n, _p(gstash))
+    gstash = torch.empty((7, n, 256), dtype=torch.bfloat16, device=out.device) if want_gstash else None
+    gpoints = torch.empty((n, 3), dtype=torch.float32, device=out.device) if xyz_w is not None else None
+    a = L.SgSdfnetBwdArgs(_p(gout), _p(out), _p(mask_stash), _p(wt_img), _p(w8), n, _p(gstash), _p(gpoints), _p(xyz_w))
     L.check(L.lib().sg_sdfnet_bwd(ctypes.byref(a), stream()), 'sg_sdfnet_bwd')
-    return gstash
+    return (gstash, gpoints) if xyz_w is not None else gstash
+
+
+def sdfnet_infer(w_img, aux, n, out=None, points=None, ray_index=None, n_ptr=None, grid_r=0, grid_axis=None, mask_stash=None, trace=None):
+    """Single-latent fused forward (sg_sdfnet_infer).  `trace` = dict(points, dirs, hit, next_index, next_count, sdf_offset, clamp,
+    threshold, radius, miss_y) turns the call into one sphere-tracing step."""
+    a = L.SgSdfnetInferArgs()
+    a.points, a.n, a.n_ptr, a.ray_index = _p(points), n, _p(n_ptr), _p(ray_index)
+    a.grid_r, a.grid_axis = grid_r, _p(grid_axis)
+    a.w_img, a.aux, a.out, a.mask_stash = _p(w_img), _p(aux), _p(out), _p(mask_stash)
+    if trace is not None:
+        a.trace_points, a.trace_dirs, a.trace_hit = _p(trace['points']), _p(trace['dirs']), _p(trace['hit'])
+        a.next_index, a.next_count = _p(trace['next_index']), _p(trace['next_count'])
+        a.sdf_offset, a.trace_clamp, a.trace_threshold, a.trace_radius = trace['sdf_offset'], trace['clamp'], trace['threshold'], trace['radius']
+        a.trace_miss_y = 1 if trace.get('miss_y') else 0
+    L.check(L.lib().sg_sdfnet_infer(ctypes.byref(a), stream()), 'sg_sdfnet_infer')
+    return out
+
+
+def grid_sphere_index(r, axis, radius):
+    """int32 list (sorted) of the cells of the R^3 grid inside the sphere; `axis` fp32 [3, r] on the device"""
+    idx = torch.empty(r * r * r, dtype=torch.int32, device=axis.device)
+    count = torch.zeros(1, dtype=torch.int32, device=axis.device)
+    _call('sg_grid_sphere_index', r, _p(axis), float(radius), _p(idx), _p(count))
+    return torch.sort(idx[:int(count.item())]).values.contiguous()
+
+
+def voxel_ingest(src, clamp=0.1, rescale=True, out=None):
+    out = torch.empty_like(src) if out is None else out
+    _call('sg_voxel_ingest', _p(src), _p(out), src.numel(), float(clamp), 1 if rescale else 0)
+    return out

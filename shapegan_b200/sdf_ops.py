@@ -58,13 +58,61 @@ def _fused_pack(w, b):
     for i in (5, 6):
         put(w[i].detach(), 256)
     assert off == 28 * chunk
-    # per column pair (c, c+1): {wx_c, wx_c1, wy_c, wy_c1, wz_c, wz_c1, b_c, b_c1} -- the fma.rn.f32x2 operand order of sg_sdfnet.cu
-    xb1 = torch.cat((w1[:, 0:3], b[0].detach().unsqueeze(1)), 1).reshape(128, 2, 4).permute(0, 2, 1)
-    xb5 = torch.cat((w5[:, 256:259], b[4].detach().unsqueeze(1)), 1).reshape(128, 2, 4).permute(0, 2, 1)
-    aux = torch.cat([xb1.reshape(-1), xb5.reshape(-1)] + [b[i].detach() for i in (1, 2, 3, 5, 6)] +
-                    [w[7].detach().reshape(-1), b[7].detach().reshape(-1)]).contiguous().float()
+    aux = _aux_block(w, b, b[0].detach(), b[4].detach())
     PACK_CACHE.put(key, sig, (img, aux))
     return img, aux
+
+
+def _aux_block(w, b, bias1, bias5):
+    """fp32 aux block of sg_sdfnet.cu; `bias1` / `bias5` are the bias vectors layers1.0 / layers2.0 start from."""
+    w1, w5 = w[0].detach(), w[4].detach()
+    # per column pair (c, c+1): {wx_c, wx_c1, wy_c, wy_c1, wz_c, wz_c1, b_c, b_c1} -- the fma.rn.f32x2 operand order of sg_sdfnet.cu
+    xb1 = torch.cat((w1[:, 0:3], bias1.unsqueeze(1)), 1).reshape(128, 2, 4).permute(0, 2, 1)
+    xb5 = torch.cat((w5[:, 256:259], bias5.unsqueeze(1)), 1).reshape(128, 2, 4).permute(0, 2, 1)
+    return torch.cat([xb1.reshape(-1), xb5.reshape(-1)] + [b[i].detach() for i in (1, 2, 3, 5, 6)] +
+                     [w[7].detach().reshape(-1), b[7].detach().reshape(-1)]).contiguous().float()
+
+
+def folded_enabled(latent_size):
+    """single-latent inference rides the fused kernel: bf16 mode, latent_code_size 128 (the fused kernel's weight image)"""
+    return config.planes() == 1 and latent_size == 128 and fused_enabled()
+
+
+def folded_weights(params, latent_code):
+    """(weight image, aux) for single-latent inference: the latent part of layers1.0 / layers2.0 is the constant vector
+    W[:, latent] z (model/sdf_net.py:57,59 with one z for every point), folded in fp32 into those layers' bias slots -- the kernel
+    then streams no latent chunks and layers1.0 needs no MMA at all."""
+    w = [params[2 * i] for i in range(8)]
+    b = [params[2 * i + 1] for i in range(8)]
+    img, _ = _fused_pack(w, b)
+    z = latent_code.detach().reshape(-1).float()
+    w1, w5 = w[0].detach(), w[4].detach()
+    bias1 = b[0].detach() + (w1[:, 3:131] * z).sum(1)
+    bias5 = b[4].detach() + (w5[:, 259:387] * z).sum(1)
+    return img, _aux_block(w, b, bias1, bias5)
+
+
+def infer_single_latent(params, latent_code, **kw):
+    img, aux = folded_weights(params, latent_code)
+    return raw.sdfnet_infer(img, aux, **kw)
+
+
+def normals_single_latent(params, latent_code, points, normalize=True):
+    """SDFNet.get_normals (model/sdf_net.py:118-128) without autograd: folded forward that keeps only the 1-bit ReLU masks, then the
+    fused backward chain with the xyz gradient accumulated inside its drains.  Returns (sdf [n], d sdf / d xyz [n, 3])."""
+    w = [params[2 * i] for i in range(8)]
+    n = points.shape[0]
+    dev = points.device
+    img, aux = folded_weights(params, latent_code)
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    mstash = torch.empty((7, n, 8), dtype=torch.int32, device=dev)
+    raw.sdfnet_infer(img, aux, n, out=out, points=points, mask_stash=mstash)
+    xyz_w = torch.stack((w[0].detach()[:, 0:3].t(), w[4].detach()[:, 256:259].t())).contiguous().float()
+    gout = torch.ones(n, dtype=torch.float32, device=dev)
+    _, g = raw.sdfnet_bwd(gout, out, mstash, _fused_pack_t(w), w[7].detach().reshape(-1), xyz_w=xyz_w, want_gstash=False)
+    if normalize:
+        g /= torch.norm(g, dim=1).unsqueeze(dim=1)
+    return out, g
 
 
 class SDFNetFunction(Function):

@@ -181,3 +181,27 @@ def test_autoencoder(variational):
     with torch.no_grad():
         o = R.autoencoder_forward(sd, x, variational, False)
         assert rel_l2(o[0] if variational else o, g['out_eval']) < TOL
+
+
+def test_render_oracle_pinned_to_chairs_golden():
+    """oracle/ref_render.py: voxelise() reproduces the reference's chairs grid evaluation; march() / normals() are consistent with it
+    (a marched hit point has |sdf| below the threshold band, normals are unit length and point along increasing sdf)."""
+    from oracle import ref_render as RR
+    g = load_golden('sdfnet_chairs')
+    sd = {k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('w.')}
+    z = torch.from_numpy(g['z'])
+    full = RR.voxelise(sd, z, 32, sphere_only=False, pad=False)
+    assert rel_l2(torch.from_numpy(full).reshape(-1), g['out']) < TOL
+    vox = RR.voxelise(sd, z, 32, sphere_only=True)
+    mask, _ = RR.sphere_mask(32)
+    m3 = mask.reshape(32, 32, 32)
+    assert int(mask.sum()) == 20360 and np.all(vox[~m3] == 1.0) and np.allclose(vox[m3], full[m3], atol=1e-6)
+    pts = torch.tensor([[0.9, 0.0, 0.0], [0.0, 0.9, 0.1], [-0.8, 0.2, 0.3]])
+    sdf, nrm = RR.normals(sd, z, pts)
+    assert torch.allclose(nrm.norm(dim=1), torch.ones(3), atol=1e-5)
+    eps = 1e-3
+    sdf2 = R.sdfnet_forward(sd, pts + eps * nrm, z.reshape(1, -1).repeat(3, 1))
+    assert torch.all(sdf2 > sdf)                                   # the normal is the direction of increasing distance
+    # ingest == datasets.py:16-23
+    raw = np.array([0.3, -0.2, 0.05, 0.1], dtype=np.float32)
+    assert torch.equal(RR.ingest(raw), torch.tensor([1.0, -1.0, np.float32(0.05) / np.float32(0.1), 1.0]))
