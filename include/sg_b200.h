@@ -265,6 +265,27 @@ int sg_grid_sphere_index(int r, const float* axis, float radius, int32_t* index_
 /* VoxelDataset.__getitem__ (datasets.py:16-23) on a whole raw batch: dst = clamp(src, -clamp, clamp) [/ clamp], float32, bit-exact */
 int sg_voxel_ingest(const float* src, float* dst, int64_t n, float clamp, int rescale, void* stream);
 
+/* GPU marching cubes (replaces skimage.measure.marching_cubes_lewiner at model/sdf_net.py:103): volume fp32 [nx][ny][nz] (z fastest),
+ * inside = value < level, vertices on the crossing cell edges (linear interpolation, index space x spacing), faces oriented towards
+ * increasing value, per-vertex normals from the interpolated central-difference gradient.  Two calls around one host read:
+ *   sg_mc_count : fills block_sums (uint64 [sg_mc_workspace_entries]); its LAST entry = #vertices (low 32 bits) | #faces << 32
+ *   sg_mc_emit  : with vertices [V][3], normals [V][3], faces [F][3] and vbase int32 [nx*ny*nz] allocated by the caller
+ * Output order is deterministic (grid order); the case table is generated (oracle/mc_tables.py -> csrc/sg_mc_tables.h). */
+typedef struct {
+  const float* volume;
+  int32_t nx, ny, nz;
+  float level;
+  float spacing[3];
+  void* block_sums;
+  int32_t* vbase;
+  float* vertices;
+  float* normals;
+  int32_t* faces;
+} sg_mc_args;
+size_t sg_mc_workspace_entries(int nx, int ny, int nz);
+int sg_mc_count(const sg_mc_args* a, void* stream);
+int sg_mc_emit(const sg_mc_args* a, void* stream);
+
 /* ---- misc ---- */
 int sg_abi_version(void);
 const char* sg_last_error(void);

@@ -55,6 +55,11 @@ class SgSdfnetBwdArgs(ctypes.Structure):
                 ('n', c_int64), ('gstash', c_void_p), ('gpoints', c_void_p), ('xyz_w', c_void_p)]
 
 
+class SgMcArgs(ctypes.Structure):
+    _fields_ = [('volume', c_void_p), ('nx', c_int32), ('ny', c_int32), ('nz', c_int32), ('level', c_float), ('spacing', c_float * 3),
+                ('block_sums', c_void_p), ('vbase', c_void_p), ('vertices', c_void_p), ('normals', c_void_p), ('faces', c_void_p)]
+
+
 class SgSdfnetInferArgs(ctypes.Structure):
     _fields_ = [('points', c_void_p), ('n', c_int64), ('n_ptr', c_void_p), ('ray_index', c_void_p), ('grid_r', c_int32),
                 ('grid_axis', c_void_p), ('w_img', c_void_p), ('aux', c_void_p), ('out', c_void_p), ('mask_stash', c_void_p),
@@ -84,6 +89,9 @@ SYMBOLS = {
     'sg_sdfnet_fwd_layout': (c_int32, [ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
     'sg_sdfnet_bwd': (c_int32, [ctypes.POINTER(SgSdfnetBwdArgs), c_void_p]),
     'sg_sdfnet_infer': (c_int32, [ctypes.POINTER(SgSdfnetInferArgs), c_void_p]),
+    'sg_mc_workspace_entries': (c_size_t, [c_int32, c_int32, c_int32]),
+    'sg_mc_count': (c_int32, [ctypes.POINTER(SgMcArgs), c_void_p]),
+    'sg_mc_emit': (c_int32, [ctypes.POINTER(SgMcArgs), c_void_p]),
     # p = pointer, l = int64, i = int32, f = float (see _sig)
     'sg_act_bwd': 'plplpliliipp',
     'sg_bn_stats': 'plilipp',

@@ -175,13 +175,13 @@ class SDFNet(SavableModule):
         return voxels
 
     def get_mesh(self, latent_code, voxel_resolution=64, sphere_only=True, raise_on_empty=False, level=0):
-        import skimage.measure          # lazy: only needed here (model/sdf_net.py:2-3 imports them at module level)
-        import trimesh
+        """:97-113 with the GPU marching cubes of shapegan_b200.mesh in place of skimage.measure.marching_cubes_lewiner.  Returns a
+        trimesh.Trimesh when trimesh is installed (the reference's return type), else a minimal object with the same three fields."""
+        from ..mesh import Mesh, marching_cubes
         size = 2
         voxels = self.get_voxels(latent_code, voxel_resolution=voxel_resolution, sphere_only=sphere_only)
         voxels = np.pad(voxels, 1, mode='constant', constant_values=1)
         spacing = (size / voxel_resolution,) * 3
-        marching_cubes = getattr(skimage.measure, 'marching_cubes_lewiner', None) or skimage.measure.marching_cubes
         try:
             vertices, faces, normals, _ = marching_cubes(voxels, level=level, spacing=spacing)
         except ValueError as value_error:
@@ -189,6 +189,10 @@ class SDFNet(SavableModule):
                 raise value_error
             return None
         vertices -= size / 2
+        try:
+            import trimesh
+        except ImportError:
+            return Mesh(vertices, faces, normals)
         return trimesh.Trimesh(vertices=vertices, faces=faces, vertex_normals=normals)
 
     def get_uniform_surface_points(self, latent_code, point_count=1000, voxel_resolution=64, sphere_only=True, level=0):

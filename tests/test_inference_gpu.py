@@ -165,3 +165,22 @@ def test_voxel_ingest_bit_exact():
         assert torch.equal(got, want), (clamp, rescale)
     odd = torch.randn((1003,), generator=g)                      # length not a multiple of 4
     assert torch.equal(raw.voxel_ingest(odd.cuda()).cpu(), RR.ingest(odd.numpy()))
+
+
+def test_voxel_batch_stream_matches_dataset(tmp_path):
+    """VoxelBatchStream (pinned staging -> side-stream H2D -> sg_voxel_ingest) delivers exactly what VoxelDataset.__getitem__ +
+    DataLoader collation deliver (datasets.py:16-23), incl. the short last batch."""
+    from shapegan_b200.data import VoxelDataset
+    g = torch.Generator().manual_seed(11)
+    files = []
+    for i in range(11):
+        f = str(tmp_path / ('%03d.npy' % i))
+        np.save(f, (torch.randn((16, 16, 16), generator=g) * 0.07).numpy())
+        files.append(f)
+    ds = VoxelDataset(files)
+    want = torch.stack([ds[i] for i in range(len(ds))])
+    got = torch.cat([b.clone() for b in ds.stream(4, shuffle=False)]).cpu()
+    assert got.shape == want.shape and torch.equal(got, want)
+    assert len(ds.stream(4)) == 3 and len(ds.stream(4, drop_last=True)) == 2
+    seen = torch.cat([b.clone() for b in ds.stream(4, shuffle=True, seed=3)]).cpu()
+    assert torch.equal(seen.sum(dim=(1, 2, 3)).sort().values, want.sum(dim=(1, 2, 3)).sort().values)      # a permutation of the same items
