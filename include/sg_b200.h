@@ -91,6 +91,9 @@ typedef struct {
   int32_t merge_n;    /* 1: one MMA spans all N atoms (LBO stride); 0: one MMA per 64-column atom */
   float* partials;    /* [ksplit][m_pad][n_total] fp32 workspace, m_pad = roundup(a.c,128), n_total = taps*b.c */
   int32_t ksplit_out; /* filled by sg_wgrad_plan */
+  float* bias_partials;   /* optional [ksplit][m_pad] fp32: column sums of A per split (A = dY: the bias gradient), produced by one extra
+                             N = 16 MMA per K step against a tile of ones; fold with sg_wgrad_reduce (taps = 1, cb = 1, sm = 1) */
+  int32_t bias_ws_floats; /* filled by sg_wgrad_plan: floats bias_partials must hold */
 } sg_wgrad_args;
 int sg_wgrad_plan(sg_wgrad_args* a, size_t* workspace_bytes); /* fills ksplit, returns bytes for partials */
 int sg_wgrad(const sg_wgrad_args* a, void* stream);

@@ -29,7 +29,8 @@ class SgIgemmArgs(ctypes.Structure):
 
 class SgWgradArgs(ctypes.Structure):
     _fields_ = [('b_mode', c_int32), ('planes', c_int32), ('a', SgTensor), ('b', SgTensor), ('rows', c_int64),
-                ('ksplit', c_int32), ('merge_n', c_int32), ('partials', c_void_p), ('ksplit_out', c_int32)]
+                ('ksplit', c_int32), ('merge_n', c_int32), ('partials', c_void_p), ('ksplit_out', c_int32),
+                ('bias_partials', c_void_p), ('bias_ws_floats', c_int32)]
 
 
 class SgWgradReduceArgs(ctypes.Structure):

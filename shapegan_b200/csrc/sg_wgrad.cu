@@ -27,6 +27,8 @@ struct WgradP {
   long long rows; int row_tiles, rs;          // rs = rows per stage (128 / planes)
   int taps, n_total, n_groups, m_tiles, m_pad, ksplit, merge_n;
   float* partials;
+  float* bias_partials;      // optional [ksplit][m_pad]: column sums of A (= the bias gradient when A is dY), one extra N = 16 MMA per K step
+                             // against a constant tile of ones -- the activations are not read a second time for it
   int stages; unsigned stage_bytes, tile_bytes;
   long long work_total;
   int* err;
@@ -64,6 +66,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
   }
   const int tps = (p.row_tiles + p.ksplit - 1) / p.ksplit;    // row tiles (stages) per split
   const int rpi = p.rs / 16;                                   // rows handled per producer thread per atom
+  // bias mode: one accumulator buffer (columns 0..255) + the 16 bias columns at 256; a 2 KB block of bf16 ones behind the stages
+  // serves every K step as the MN-major B operand (all elements equal: the swizzle is irrelevant)
+  const bool bias_mode = p.bias_partials != nullptr;
+  uint8_t* ones_tile = stage0 + (size_t)S * p.stage_bytes;
+  if (bias_mode) {
+    for (int i = tid; i < 512; i += kWgThreads) reinterpret_cast<uint32_t*>(ones_tile)[i] = 0x3f803f80u;
+    fence_proxy_async();
+    __syncthreads();
+  }
 
   if (warp < 4 && p.use_tma) {
     // ================================================================ TMA PRODUCER (warp 0, one elected lane issues): every atom is one box
@@ -262,13 +273,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
       const int ks = (int)(w % p.ksplit);
       const int ng = (int)((w / p.ksplit) % p.n_groups);
       const int nb_atoms = min(kAtomsB, (p.n_total - ng * 256) / 64);
-      const int ab = it & 1;
-      const uint32_t aph = (uint32_t)((it >> 1) & 1);
+      const int ab = bias_mode ? 0 : (it & 1);
+      const uint32_t aph = (uint32_t)(bias_mode ? (it & 1) : ((it >> 1) & 1));
       mbar_wait(&hdr->accempty[ab], aph ^ 1, p.err);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(ab * 256);
       const uint32_t idesc_full = umma_idesc(128, nb_atoms * 64, true, true);
       const uint32_t idesc_atom = umma_idesc(128, 64, true, true);
+      const uint32_t idesc_bias = umma_idesc(128, 16, true, true);
+      const bool do_bias = bias_mode && ng == 0;
       const int t0 = ks * tps, t1 = min(p.row_tiles, t0 + tps);
       for (int rt = t0; rt < t1; ++rt) {
         mbar_wait(&hdr->full[s], ph, p.err);
@@ -301,6 +314,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
                 }
               }
             }
+            if (do_bias) {
+              const uint64_t dones = umma_desc(smem_u32(ones_tile), atom_stride, 1024);
+              umma_bf16(tmem_base + 256, da, dones, idesc_bias, acc);
+              if (p.planes == 2) umma_bf16(tmem_base + 256, da_lo, dones, idesc_bias, 1u);
+            }
           }
           umma_commit(&hdr->empty[s]);
         }
@@ -320,8 +338,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
       const int ng = (int)((w / p.ksplit) % p.n_groups);
       const int mtile = (int)(w / ((long long)p.ksplit * p.n_groups));
       const int nb_atoms = min(kAtomsB, (p.n_total - ng * 256) / 64);
-      const int ab = it & 1;
-      const uint32_t aph = (uint32_t)((it >> 1) & 1);
+      const int ab = bias_mode ? 0 : (it & 1);
+      const uint32_t aph = (uint32_t)(bias_mode ? (it & 1) : ((it >> 1) & 1));
       mbar_wait(&hdr->accfull[ab], aph, p.err);
       tc_fence_after();
       float* orow = p.partials + ((size_t)ks * p.m_pad + (size_t)mtile * 128 + trow) * p.n_total + (size_t)ng * 256;
@@ -339,6 +357,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
           if (t1 <= t0) v = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(orow + c0 + j) = v;
         }
+      }
+      if (bias_mode && ng == 0) {
+        uint32_t rb16[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + 256u, rb16);
+        tmem_ld_wait();
+        p.bias_partials[(size_t)ks * p.m_pad + (size_t)mtile * 128 + trow] = (t1 <= t0) ? 0.f : __uint_as_float(rb16[0]);
       }
       tc_fence_before();
       mbar_arrive(&hdr->accempty[ab]);
@@ -393,7 +418,7 @@ static int wgrad_geometry(const sg_wgrad_args* a, WgradP& p) {
   p.n_groups = (p.n_total + 255) / 256;
   p.tile_bytes = (unsigned)(p.rs * 128);
   p.stage_bytes = (unsigned)((kAtomsA + kAtomsB) * a->planes) * p.tile_bytes;
-  p.stages = std::min<int>(kWgMaxStages, (int)((227u * 1024u - kWgHeader) / p.stage_bytes));
+  p.stages = std::min<int>(kWgMaxStages, (int)((227u * 1024u - kWgHeader - 2048u) / p.stage_bytes));   // 2 KB: the bias mode's tile of ones
   if (p.stages < 2) return sg_fail(-9, "sg_wgrad: stage does not fit");
   return 0;
 }
@@ -423,6 +448,7 @@ extern "C" int sg_wgrad_plan(sg_wgrad_args* a, size_t* workspace_bytes) {
   }
   a->ksplit_out = ksplit;
   if (workspace_bytes) *workspace_bytes = (size_t)ksplit * p.m_pad * p.n_total * sizeof(float);
+  a->bias_ws_floats = ksplit * p.m_pad;
   return 0;
 }
 
@@ -436,6 +462,7 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
   p.b_ptr = (const char*)a->b.ptr; p.b_ps = a->b.plane_stride;
   p.ksplit = a->ksplit_out; p.merge_n = a->merge_n;
   p.partials = a->partials;
+  p.bias_partials = a->bias_partials;
   p.work_total = (long long)p.m_tiles * p.n_groups * p.ksplit;
   p.err = sg_error_word();
   p.use_tma = 0;
@@ -473,7 +500,7 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
       p.use_tma = ok ? 1 : 0;
     }
   }
-  const size_t smem = kWgHeader + (size_t)p.stages * p.stage_bytes;
+  const size_t smem = kWgHeader + (size_t)p.stages * p.stage_bytes + 2048;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -166,15 +166,18 @@ class ConvOp(LinOp):
                   out_dims=(2 * d, 2 * h, 2 * wd))
         return gx
 
-    def wgrad(self, x, g, w_shape, into=None):
+    bias_in_wgrad = True     # A operand of the weight-gradient GEMM is dY: its column sums (the bias gradient) come out of the same pass
+
+    def wgrad(self, x, g, w_shape, into=None, bias_into=None):
         p, b, d, h, wd, c = x.shape
         gw = into if into is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         raw.wgrad(L.MODE_CONV, p, g, self.cout, x, (b, d, h, wd, c), g[0].numel() // self.cout, gw,
-                  sm=self.cin * 64, st=1, sc=64, m_valid=self.cout, accumulate=into is not None)
+                  sm=self.cin * 64, st=1, sc=64, m_valid=self.cout, accumulate=into is not None,
+                  bias_grad=bias_into, bias_accumulate=True)
         return gw
 
-    def wgrad_into(self, x, g, grad):
-        self.wgrad(x, g, None, into=grad)
+    def wgrad_into(self, x, g, grad, bias_into=None):
+        self.wgrad(x, g, None, into=grad, bias_into=bias_into)
 
     def out_channels(self):
         return self.cout
@@ -407,8 +410,11 @@ class _Fwd(Function):
         # first-order backward with an allocated bias .grad (flat gradient arena): the bias sums accumulate in place, like the
         # weight gradient below -- no temporary, no AccumulateGrad add kernel
         b_into = _into_grad(ctx.bias_obj, c) if want_b else None
+        # arena backward of a layer whose weight-gradient GEMM has dY as its A operand: the bias column sums ride that GEMM
+        bias_via_wgrad = (b_into is not None and getattr(op, 'bias_in_wgrad', False) and ctx.needs_input_grad[2]
+                          and _into_grad(w) is not None)
         if ctx.act != ACT_NONE:
-            g, gb_fused = _MaskMul.apply(gy, y, ctx.act, c, want_b, b_into)      # activation backward + bias column sums: one pass
+            g, gb_fused = _MaskMul.apply(gy, y, ctx.act, c, want_b and not bias_via_wgrad, b_into)      # activation backward (+ bias column sums)
         else:
             g = gy
         gx = _Tr.apply(op, g, w) if ctx.needs_input_grad[1] else None
@@ -418,11 +424,14 @@ class _Fwd(Function):
             if w_into is not None:
                 # first-order backward of a Step class with an allocated .grad (the flat gradient arena): accumulate in place,
                 # exactly what AccumulateGrad would do with the returned tensor, minus the temporary and the extra add kernel
-                op.wgrad_into(x, g, w_into)
+                if bias_via_wgrad:
+                    op.wgrad_into(x, g, w_into, bias_into=b_into)
+                else:
+                    op.wgrad_into(x, g, w_into)
             else:
                 gw = _Wgrad.apply(op, x, g, w)
         gb = None
-        if want_b:
+        if want_b and not bias_via_wgrad:
             # the bias gradient is never differentiated again on this path (the GP contributes exactly zero to biases)
             if gb_fused is not None:
                 gb = None if b_into is not None else gb_fused

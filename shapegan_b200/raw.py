@@ -149,8 +149,9 @@ def igemm(mode, planes, a, a_dims, rows, k, b_img, n_valid, out, out_ld, out_kin
 
 
 def wgrad(b_mode, planes, a, a_c, b, b_dims, rows, grad, sm, st, sc, m_valid, cb=None, taps=None, accumulate=False,
-          scale=1.0, merge_n=1, ksplit=0, c_valid=0):
-    """grad[m*sm + tap*st + c*sc] (+)= sum_rows A[row,m] * gather(B)[row(+tap), c]."""
+          scale=1.0, merge_n=1, ksplit=0, c_valid=0, bias_grad=None, bias_accumulate=False):
+    """grad[m*sm + tap*st + c*sc] (+)= sum_rows A[row,m] * gather(B)[row(+tap), c].
+    bias_grad (fp32 [m_valid]): additionally (+)= the column sums of A -- the bias gradient when A is dY -- from the same pass over A."""
     _require_cuda(a, b, grad)
     n, d, h, w, c = b_dims
     args = L.SgWgradArgs()
@@ -162,6 +163,10 @@ def wgrad(b_mode, planes, a, a_c, b, b_dims, rows, grad, sm, st, sc, m_valid, cb
     L.check(L.lib().sg_wgrad_plan(ctypes.byref(args), ctypes.byref(nbytes)), 'sg_wgrad_plan')
     ws = torch.empty(max(nbytes.value // 4, 1), dtype=torch.float32, device=grad.device)
     args.partials = ctypes.c_void_p(ws.data_ptr())
+    bws = None
+    if bias_grad is not None:
+        bws = torch.empty(max(args.bias_ws_floats, 1), dtype=torch.float32, device=grad.device)
+        args.bias_partials = ctypes.c_void_p(bws.data_ptr())
     L.check(L.lib().sg_wgrad(ctypes.byref(args), stream()), 'sg_wgrad')
     if b_mode == L.MODE_PATCH:
         taps_r, cb_r = 1, 64
@@ -173,6 +178,10 @@ def wgrad(b_mode, planes, a, a_c, b, b_dims, rows, grad, sm, st, sc, m_valid, cb
     r = L.SgWgradReduceArgs(ctypes.c_void_p(ws.data_ptr()), args.ksplit_out, round_up(a_c, 128), m_valid, taps_r, cb_r,
                             sm, st, sc, ctypes.c_void_p(grad.data_ptr()), 1 if accumulate else 0, scale, c_valid)
     L.check(L.lib().sg_wgrad_reduce(ctypes.byref(r), stream()), 'sg_wgrad_reduce')
+    if bws is not None:
+        rb = L.SgWgradReduceArgs(ctypes.c_void_p(bws.data_ptr()), args.ksplit_out, round_up(a_c, 128), m_valid, 1, 1, 1, 0, 0,
+                                 ctypes.c_void_p(bias_grad.data_ptr()), 1 if bias_accumulate else 0, scale, 0)
+        L.check(L.lib().sg_wgrad_reduce(ctypes.byref(rb), stream()), 'sg_wgrad_reduce(bias)')
     return grad
 
 

@@ -297,19 +297,25 @@ def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, ind
     gst = raw.sdfnet_bwd(gout, out, mstash, _fused_pack_t(w), w[7].detach().reshape(-1))
     g = [gst[i].unsqueeze(0) for i in range(7)]                                     # g[i]: gradient w.r.t. the pre-activation of layer i+1
     for i in range(7):
+        # the bias gradient (column sums of g_i) rides the weight-gradient GEMM of the same layer: one extra N = 16 MMA per K step against
+        # a tile of ones instead of a second pass over the 512 B/point g stash
+        bias_here = need_b[i] and need_w[i]
         if need_b[i]:
-            _, sums = raw.act_bwd(g[i], None, L.ACT_NONE, HID, want_sums=True, want_g=False)
-            gb[i] = raw.emit_sums(sums, f32((HID,)), HID)
+            gb[i] = f32((HID,))
+            if not bias_here:
+                _, sums = raw.act_bwd(g[i], None, L.ACT_NONE, HID, want_sums=True, want_g=False)
+                raw.emit_sums(sums, gb[i], HID)
         if not need_w[i]:
             continue
         gw[i] = f32(w[i].shape)
+        bg = gb[i] if bias_here else None
         if i == 0:
-            _wgrad_input(planes, g[0], x_in, cin, cin8, n, gw[0], cin)
+            _wgrad_input(planes, g[0], x_in, cin, cin8, n, gw[0], cin, bias_grad=bg)
         elif i == 4:       # W5 = [hidden 256 | xyz 3 | latent L]  (sdf_net.py:59)
-            raw.wgrad(L.MODE_DENSE, planes, g[4], HID, hs[3], (1, 1, 1, 1, HID), n, gw[4], sm=HID + cin, st=0, sc=1, m_valid=HID)
+            raw.wgrad(L.MODE_DENSE, planes, g[4], HID, hs[3], (1, 1, 1, 1, HID), n, gw[4], sm=HID + cin, st=0, sc=1, m_valid=HID, bias_grad=bg)
             _wgrad_input(planes, g[4], x_in, cin, cin8, n, gw[4][:, HID:], HID + cin)
         else:
-            raw.wgrad(L.MODE_DENSE, planes, g[i], HID, hs[i - 1], (1, 1, 1, 1, HID), n, gw[i], sm=HID, st=0, sc=1, m_valid=HID)
+            raw.wgrad(L.MODE_DENSE, planes, g[i], HID, hs[i - 1], (1, 1, 1, 1, HID), n, gw[i], sm=HID, st=0, sc=1, m_valid=HID, bias_grad=bg)
     gpoints = glatent = None
     if need_points or need_latent:
         img = PACK_CACHE.get(w[0], 'sdf_t0', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8))
@@ -329,10 +335,11 @@ def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, ind
     return tuple(grads)
 
 
-def _wgrad_input(planes, g, x_in, cin, cin8, n, grad_view, ld):
+def _wgrad_input(planes, g, x_in, cin, cin8, n, grad_view, ld, bias_grad=None):
     """dW[:, input columns] = g^T x_in  where x_in has cin8 (multiple of 8) physical columns, cin valid.
     sg_wgrad needs a column count that is a multiple of 64; the reduce only emits the valid columns."""
-    raw.wgrad(L.MODE_DENSE, planes, g, HID, x_in, (1, 1, 1, 1, cin8), n, grad_view, sm=ld, st=0, sc=1, m_valid=HID, c_valid=cin)
+    raw.wgrad(L.MODE_DENSE, planes, g, HID, x_in, (1, 1, 1, 1, cin8), n, grad_view, sm=ld, st=0, sc=1, m_valid=HID, c_valid=cin,
+              bias_grad=bias_grad)
 
 
 def sdfnet_apply(points, latent, index, params):

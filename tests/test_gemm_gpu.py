@@ -271,3 +271,32 @@ def test_splitk_partial_slabs(mode, b, r, cin, cout, ks, planes, monkeypatch):
     assert outs[0][1] == 2 and outs[1][1] == 1, 'expected main + finish kernel vs a single launch, got %s' % ([o[1] for o in outs],)
     report('splitk %s p%d ks%d' % (mode, planes, ks), outs[0][0], outs[1][0], 4e-3 if planes == 1 else 2e-5)
     check_error_word()
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+def test_wgrad_bias_sums_ride_the_gemm(planes):
+    """bias_grad = column sums of the A operand (dY) out of the weight-gradient GEMM itself (one N = 16 MMA per K step against a tile of
+    ones): dense and conv gathers, several N groups, ragged rows, M not a multiple of 128, accumulation into an existing gradient; the
+    weight gradient of the same call must be unchanged."""
+    L, raw = _imports()
+    for rows, cin, cout in ((1000, 192, 256), (77, 64, 200), (5000, 256, 256)):
+        x, dy = rnd((rows, cin), 1), rnd((rows, cout), 2)
+        g = torch.zeros((cout, cin), dtype=torch.float32, device='cuda')
+        gb = torch.full((cout,), 0.5, dtype=torch.float32, device='cuda')
+        raw.wgrad(L.MODE_DENSE, planes, raw.to_planes(dy, planes), cout, raw.to_planes(x, planes), (1, 1, 1, 1, cin), rows, g,
+                  sm=cin, st=0, sc=1, m_valid=cout, bias_grad=gb, bias_accumulate=True)
+        report('wgrad-bias dense W p%d %s' % (planes, (rows, cin, cout)), g, q(dy, planes).t() @ q(x, planes), TOL_F32)
+        report('wgrad-bias dense b p%d %s' % (planes, (rows, cin, cout)), gb, q(dy, planes).sum(0) + 0.5, TOL_F32)
+    b, r, cin, cout = 2, 8, 64, 128
+    x = rnd((b, r, r, r, cin), 3)
+    dy = rnd((b, r // 2, r // 2, r // 2, cout), 4)
+    rows = b * (r // 2) ** 3
+    g = torch.zeros((cout, cin, 4, 4, 4), dtype=torch.float32, device='cuda')
+    gb = torch.zeros((cout,), dtype=torch.float32, device='cuda')
+    raw.wgrad(L.MODE_CONV, planes, raw.to_planes(dy, planes), cout, raw.to_planes(x, planes), (b, r, r, r, cin), rows, g,
+              sm=cin * 64, st=1, sc=64, m_valid=cout, bias_grad=gb)
+    wref = torch.zeros((cout, cin, 4, 4, 4), dtype=torch.float64, device='cuda', requires_grad=True)
+    F.conv3d(q(x, planes).permute(0, 4, 1, 2, 3), wref, None, stride=2, padding=1).backward(q(dy, planes).permute(0, 4, 1, 2, 3))
+    report('wgrad-bias conv W p%d' % planes, g, wref.grad, TOL_F32)
+    report('wgrad-bias conv b p%d' % planes, gb, q(dy, planes).reshape(-1, cout).sum(0), TOL_F32)
+    check_error_word()
