@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 T0=$(date +%s)
 if [[ " $* " == *" record "* ]]; then export SG_PARITY_RECORD=1; fi
-timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; RC=$?
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; RC=$?
 unset SG_PARITY_RECORD
 echo "pytest rc=$RC $(( $(date +%s)-T0 ))s" | tee gpurun_out/times.log
 tail -5 gpurun_out/pytest_gpu.log
