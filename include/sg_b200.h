@@ -260,6 +260,14 @@ typedef struct {
 } sg_sdfnet_bwd_args;
 int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream);
 
+/* ---- non-GEMM pieces of the hand-scheduled critic update (shapegan_b200/critic.py) ----
+ * sg_gp_interp : out[b] = alpha[b] * real[b] + (1 - alpha[b]) * fake[b]          (train_hybrid_progressive_gan.py:103-105), m floats per sample
+ * sg_gp_seed   : n_b = |g_b|_2 ; *gp_sum += weight (n_b - 1)^2 / B ; v_b = 2 weight (n_b - 1) / (B n_b) g_b   (:110-111 and its derivative w.r.t. g)
+ * sg_critic_loss : out4 = {mean s[0:B] - mean s[B:2B] + gp, gp, mean s[0:B], mean s[B:2B]}   (train_wgan.py:66-68; :163) */
+int sg_gp_interp(const float* real, const float* fake, const float* alpha, float* out, int b, int64_t m, void* stream);
+int sg_gp_seed(const float* g, float* v, int b, int64_t m, float weight, double* gp_sum, void* stream);
+int sg_critic_loss(const float* scores, int b, const double* gp_sum, float* out4, void* stream);
+
 /* ---- SDFNet inference consumers / voxel data path ---- */
 /* Cells s = (ix*r + iy)*r + iz of the util.get_voxel_coordinates(r) grid (util.py:60-74) with |p| < radius, the sphere mask of
  * SDFVoxelizationHelperData (model/sdf_net.py:12-14), evaluated in numpy's float32 arithmetic operation by operation (bit-exact set).

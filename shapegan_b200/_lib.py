@@ -118,6 +118,9 @@ SYMBOLS = {
     'sg_clamp': 'plffp',
     'sg_sum_f32': 'plpp',
     'sg_l1_loss_grad': 'ppplpp',
+    'sg_gp_interp': 'ppppilp',
+    'sg_gp_seed': 'ppilfpp',
+    'sg_critic_loss': 'pippp',
     'sg_grid_sphere_index': 'ipfppp',
     'sg_voxel_ingest': 'pplfip',
 }

@@ -158,7 +158,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
               const bf16* mk = p.mask + obase + c0;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const uint4 m = __ldg(reinterpret_cast<const uint4*>(mk + j));
+                const uint4 m = *reinterpret_cast<const uint4*>(mk + j);     // plain load: `mask` may alias `out` (in-place activation backward)
                 v[j] *= act_grad_from_output(bf16lo_to_f(m.x), p.mask_act); v[j + 1] *= act_grad_from_output(bf16hi_to_f(m.x), p.mask_act);
                 v[j + 2] *= act_grad_from_output(bf16lo_to_f(m.y), p.mask_act); v[j + 3] *= act_grad_from_output(bf16hi_to_f(m.y), p.mask_act);
                 v[j + 4] *= act_grad_from_output(bf16lo_to_f(m.z), p.mask_act); v[j + 5] *= act_grad_from_output(bf16hi_to_f(m.z), p.mask_act);

@@ -150,20 +150,21 @@ class ConvOp(LinOp):
     def __init__(self, cin, cout):
         self.cin, self.cout = cin, cout
 
-    def fwd(self, x, w, bias, act):
+    def fwd(self, x, w, bias, act, out=None, mask=None, mask_act=ACT_NONE):
+        """`out` (optional) receives the result; `mask`: out *= act'(mask) (an activation backward fused into the epilogue; may alias out)"""
         p, b, d, h, wd, c = x.shape
         rows = b * (d // 2) * (h // 2) * (wd // 2)
-        y = _new((b, d // 2, h // 2, wd // 2, self.cout), x.device)
+        y = out if out is not None else _new((b, d // 2, h // 2, wd // 2, self.cout), x.device)
         img = PACK_CACHE.get(w, 'conv_fwd', p, raw.pack_conv_fwd)
-        raw.igemm(L.MODE_CONV, p, x, (b, d, h, wd, c), rows, 64 * c, img, self.cout, y, self.cout, bias=bias, act=act)
+        raw.igemm(L.MODE_CONV, p, x, (b, d, h, wd, c), rows, 64 * c, img, self.cout, y, self.cout, bias=bias, act=act, mask=mask, mask_act=mask_act)
         return y
 
-    def tr(self, g, w):
+    def tr(self, g, w, mask=None, mask_act=ACT_NONE):
         p, b, d, h, wd, c = g.shape          # g: [P,B,Do,Ho,Wo,Cout]
         gx = _new((b, 2 * d, 2 * h, 2 * wd, self.cin), g.device)
         img = PACK_CACHE.get(w, 'conv_dgrad', p, raw.pack_conv_dgrad)
         raw.igemm(L.MODE_CONVT, p, g, (b, d, h, wd, c), b * d * h * wd, 8 * c, img, self.cin, gx, self.cin,
-                  out_dims=(2 * d, 2 * h, 2 * wd))
+                  out_dims=(2 * d, 2 * h, 2 * wd), mask=mask, mask_act=mask_act)
         return gx
 
     bias_in_wgrad = True     # A operand of the weight-gradient GEMM is dY: its column sums (the bias gradient) come out of the same pass
@@ -192,14 +193,14 @@ class Conv1Op(LinOp):
         # non-zero data (progressive_gan.py:15); addressing uses its strides, the gradient of the other channels is 0.
         self.cout, self.w_cin = cout, w_cin
 
-    def fwd(self, x, w, bias, act):
+    def fwd(self, x, w, bias, act, out=None, mask=None, mask_act=ACT_NONE):
         b, d, h, wd = x.shape
         p = _planes()
         rows = b * (d // 2) * (h // 2) * (wd // 2)
-        y = _new((b, d // 2, h // 2, wd // 2, self.cout), x.device)
+        y = out if out is not None else _new((b, d // 2, h // 2, wd // 2, self.cout), x.device)
         img = PACK_CACHE.get(w, 'conv1_fwd', p, lambda t, pl: raw.pack_b(
             t, pl, self.cout, 64, 64, 1, 1, s_n0=self.w_cin * 64, s_tap=1, s_c=0))
-        raw.igemm(L.MODE_PATCH, p, x, (b, d, h, wd, 1), rows, 64, img, self.cout, y, self.cout, bias=bias, act=act)
+        raw.igemm(L.MODE_PATCH, p, x, (b, d, h, wd, 1), rows, 64, img, self.cout, y, self.cout, bias=bias, act=act, mask=mask, mask_act=mask_act)
         return y
 
     def tr(self, g, w):
@@ -212,11 +213,12 @@ class Conv1Op(LinOp):
         raw.igemm(L.MODE_DENSE, p, g, (1, 1, 1, 1, c), rows, r64(c), img, 64, pm, 64)
         return raw.col2im_c1(pm, b, d, h, wd, None, ACT_NONE)
 
-    def wgrad(self, x, g, w_shape):
+    def wgrad(self, x, g, w_shape, into=None):
+        """into: accumulate into an existing gradient (channels > 0 of a from_SDF weight receive nothing, i.e. stay as they are)"""
         b, d, h, wd = x.shape
-        gw = (torch.zeros if self.w_cin > 1 else torch.empty)(w_shape, dtype=torch.float32, device=x.device)
+        gw = into if into is not None else (torch.zeros if self.w_cin > 1 else torch.empty)(w_shape, dtype=torch.float32, device=x.device)
         raw.wgrad(L.MODE_PATCH, g.shape[0], g, self.cout, x, (b, d, h, wd, 1), g[0].numel() // self.cout, gw,
-                  sm=self.w_cin * 64, st=0, sc=1, m_valid=self.cout)
+                  sm=self.w_cin * 64, st=0, sc=1, m_valid=self.cout, accumulate=into is not None)
         return gw
 
     def out_channels(self):
@@ -310,34 +312,35 @@ class DenseOp(LinOp):
         assert self.n % 8 == 0 and self.k % 8 == 0, 'DenseOp needs N, K multiples of 8'
         assert n1 == 1 or t == 1, 'DenseOp: only one side may be two-level'
 
-    def fwd(self, x, w, bias, act):
+    def fwd(self, x, w, bias, act, out=None, mask=None, mask_act=ACT_NONE):
         p, rows = x.shape[0], x.shape[1]
-        y = _new((rows, self.n), x.device)
+        y = out if out is not None else _new((rows, self.n), x.device)
         img = PACK_CACHE.get(w, self.tag + '_f', p, lambda tt, pl: raw.pack_b(
             tt, pl, self.n, r64(self.k), self.t, self.c, self.c, s_n0=self.s_n0, s_tap=self.s_t, s_c=self.s_c,
             n0_count=self.n0, s_n1=self.s_n1))
         raw.igemm(L.MODE_DENSE, p, x, (1, 1, 1, 1, self.k), rows, r64(self.k), img, self.n, y, self.n, bias=bias, act=act,
-                  bias_mod=self.n0 if (self.n1 > 1 and bias is not None) else 0)
+                  bias_mod=self.n0 if (self.n1 > 1 and bias is not None) else 0, mask=mask, mask_act=mask_act)
         return y
 
-    def tr(self, g, w):
+    def tr(self, g, w, mask=None, mask_act=ACT_NONE):
         p, rows = g.shape[0], g.shape[1]
         gx = _new((rows, self.k), g.device)
         img = PACK_CACHE.get(w, self.tag + '_t', p, lambda tt, pl: raw.pack_b(
             tt, pl, self.k, r64(self.n), self.n1, self.n0, self.n0, s_n0=self.s_c, s_tap=self.s_n1, s_c=self.s_n0,
             n0_count=self.c, s_n1=self.s_t))
-        raw.igemm(L.MODE_DENSE, p, g, (1, 1, 1, 1, self.n), rows, r64(self.n), img, self.k, gx, self.k)
+        raw.igemm(L.MODE_DENSE, p, g, (1, 1, 1, 1, self.n), rows, r64(self.n), img, self.k, gx, self.k, mask=mask, mask_act=mask_act)
         return gx
 
-    def wgrad(self, x, g, w_shape):
+    def wgrad(self, x, g, w_shape, into=None):
         p, rows = x.shape[0], x.shape[1]
-        gw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
+        gw = into if into is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
+        acc = into is not None
         if self.n1 == 1:      # A = g (one-level n0), B = x (t, c)
             raw.wgrad(L.MODE_DENSE, p, g, self.n, x, (1, 1, 1, 1, self.k), rows, gw, sm=self.s_n0, st=self.s_t, sc=self.s_c,
-                      m_valid=self.n, taps=self.t, cb=self.c)
+                      m_valid=self.n, taps=self.t, cb=self.c, accumulate=acc)
         else:                 # A = x (one-level c), B = g (n1, n0)
             raw.wgrad(L.MODE_DENSE, p, x, self.k, g, (1, 1, 1, 1, self.n), rows, gw, sm=self.s_c, st=self.s_n1, sc=self.s_n0,
-                      m_valid=self.k, taps=self.n1, cb=self.n0)
+                      m_valid=self.k, taps=self.n1, cb=self.n0, accumulate=acc)
         return gw
 
     def out_channels(self):

@@ -18,8 +18,15 @@ Step definitions:
 import torch
 import torch.distributed as dist
 
+import os
+
 from . import raw
+from .critic import CriticUpdate
 from .ops import arena_backward
+
+
+def _fused_critic_enabled():
+    return os.environ.get('SG_B200_NO_FUSED_CRITIC') != '1'
 
 
 class FlatOptimizer:
@@ -93,6 +100,7 @@ class WGANStep:
         critic.use_sigmoid = False                                     # train_wgan.py:31
         self.gopt = FlatOptimizer(generator.parameters(), 'rmsprop', lr, world_size=world_size)
         self.copt = FlatOptimizer(critic.parameters(), 'rmsprop', lr, clip=0.0 if gp else clip, world_size=world_size)
+        self.critic_update = CriticUpdate(critic)
 
     def __call__(self, real, z_critic, z_gen, alpha=None):
         """real [B,32,32,32] fp32, z_* [B,128] fp32, alpha [B,1,1,1] (GP variant) — all on the device.
@@ -104,12 +112,17 @@ class WGANStep:
         # :66-68  critic(fake) and critic(valid) as ONE batch of 2B samples: the critic has no BatchNorm (model/gan.py:48-57), so the
         # samples are independent and mean(D(fake)) - mean(D(real)) and every gradient are the same sums, in half the launches
         b = real.shape[0]
-        score = cri(torch.cat((fake.reshape(real.shape), real), 0))
-        closs = torch.mean(score[:b]) - torch.mean(score[b:])
-        if self.gp:
-            closs = closs + gradient_penalty(cri, real, fake.squeeze(1), alpha, self.gp_weight)
-        with arena_backward():                                               # :69
-            closs.backward()
+        if _fused_critic_enabled() and self.critic_update.supported():
+            # :66-69 (+ the gradient penalty) as the hand-scheduled sweep of shapegan_b200/critic.py: no autograd graph
+            with torch.no_grad():
+                closs = self.critic_update(fake.reshape(real.shape), real, alpha if self.gp else None, self.gp_weight)[0]
+        else:
+            score = cri(torch.cat((fake.reshape(real.shape), real), 0))
+            closs = torch.mean(score[:b]) - torch.mean(score[b:])
+            if self.gp:
+                closs = closs + gradient_penalty(cri, real, fake.squeeze(1), alpha, self.gp_weight)
+            with arena_backward():                                           # :69
+                closs.backward()
         self.copt.step()                                               # :70-71 (clip fused)
         self.gopt.zero_grad(); self.copt.zero_grad()                    # :75-76
         # The reference's backward here also fills the critic's weight gradients, which :62-63 of the next batch zeroes
@@ -209,6 +222,7 @@ class HybridProgressiveStep:
         self.grid = get_voxel_coordinates(self.r, return_torch_tensor=True, device=dev)     # :95
         self.gopt = FlatOptimizer(generator.parameters(), 'rmsprop', lr, world_size=world_size)
         self.dopt = FlatOptimizer(discriminator.parameters(), 'rmsprop', lr, world_size=world_size)
+        self.critic_update = CriticUpdate(discriminator)
         self._cache = {}
 
     def generate(self, z):
@@ -236,7 +250,13 @@ class HybridProgressiveStep:
         self.gopt.zero_grad(); self.dopt.zero_grad()                                    # :153
         with torch.no_grad():                            # the reference back-propagates into G here and discards it (:136)
             fake = self.generate(z)
-        b = valid.shape[0]                               # one batch of 2B samples (no BatchNorm in the critic: same sums, half the launches)
+        b = valid.shape[0]
+        if _fused_critic_enabled() and self.critic_update.supported():
+            with torch.no_grad():                        # :157-164 as the hand-scheduled sweep of shapegan_b200/critic.py
+                out4 = self.critic_update(fake, valid, alpha, self.gp_weight)
+            self.dopt.step()                                                           # :166
+            return out4[0], out4[1]
+        # one batch of 2B samples (no BatchNorm in the critic: same sums, half the launches)
         out = self.dis(torch.cat((fake, valid), 0))                                    # :157,160
         out_fake, out_valid = out[:b], out[b:]
         gp = gradient_penalty(self.dis, valid, fake, alpha, self.gp_weight)            # :162

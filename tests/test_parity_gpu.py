@@ -582,3 +582,78 @@ def test_wgan_step_object_b64(prec):
     for k, v in cri.state_dict().items():
         check_digest(g, 'critic_after.' + k, v, 1e-3 if prec == 'fp32x' else 1e-2, atol=1.1e-3)
     check_dev()
+
+
+# ------------------------------------------------------------------------------------------------- hand-scheduled critic update
+@pytest.mark.parametrize('name', ['progressive_disc_it0_f100', 'progressive_disc_it2_f100'])
+def test_fused_critic_update_progressive_golden(prec, name):
+    """shapegan_b200.critic.CriticUpdate (forward / backward / penalty / adjoint / weight sweeps, no autograd) against the reference's
+    total gradient of  mean D(fake) - mean D(real) + gp  (train_hybrid_progressive_gan.py:157-164) on the progressive critic."""
+    from model.progressive_gan import Discriminator
+    from shapegan_b200.critic import CriticUpdate
+    g = load_golden(name)
+    c = Checker(prec, name, g)
+    d = Discriminator().cuda()
+    seeded_load(d, int(g['seed_weights']))
+    d.set_iteration(int(g['iteration']))
+    d.fade_in_progress = float(g['fade'])
+    upd = CriticUpdate(d)
+    assert upd.supported()
+    with torch.no_grad():
+        out4 = upd(cu(g['fake']), cu(g['real']), cu(g['alpha']), 10.0)
+    c.scalar('gp', out4[1].item())
+    want = float(np.mean(g['out_fake']) - np.mean(g['out_real']) + g['gp'])
+    assert abs(out4[0].item() - want) <= (2e-3 if prec == 'fp32x' else 2e-2) * max(1.0, abs(want))
+    c.params('grad.', d)
+    c.done()
+    check_dev()
+
+
+@pytest.mark.parametrize('gp', [False, True])
+def test_fused_critic_update_equals_autograd_path(prec, gp):
+    """gan.Discriminator at B=6: CriticUpdate == the twice-differentiable autograd path (itself pinned to the reference's goldens by
+    test_discriminator / test_discriminator_gradient_penalty), losses and every parameter gradient."""
+    from model.gan import Discriminator
+    from shapegan_b200 import train
+    from shapegan_b200.critic import CriticUpdate
+    b = 6
+    gen = torch.Generator().manual_seed(77)
+    real = (torch.clamp(torch.randn((b, 32, 32, 32), generator=gen) * 0.05, -0.1, 0.1) / 0.1).cuda()
+    fake = torch.tanh(torch.randn((b, 32, 32, 32), generator=gen)).cuda()
+    alpha = torch.rand((b, 1, 1, 1), generator=gen).cuda()
+    grads = []
+    for fused in (True, False):
+        dis = Discriminator()
+        seeded_load(dis, 301)
+        dis.use_sigmoid = False
+        for p in dis.parameters():
+            p.grad = torch.zeros_like(p)
+        if fused:
+            with torch.no_grad():
+                out4 = CriticUpdate(dis)(fake, real, alpha if gp else None, 10.0)
+            loss = out4[0].item()
+        else:
+            score = dis(torch.cat((fake, real), 0))
+            closs = torch.mean(score[:b]) - torch.mean(score[b:])
+            if gp:
+                closs = closs + train.gradient_penalty(dis, real, fake, alpha, 10.0)
+            closs.backward()
+            loss = closs.item()
+        grads.append((loss, {k: p.grad.clone() for k, p in dis.named_parameters()}))
+    tol = 2e-3 if prec == 'fp32x' else 4e-2
+    assert abs(grads[0][0] - grads[1][0]) <= tol * max(1.0, abs(grads[1][0]))
+    lines, bad = [], []
+    for k in grads[0][1]:
+        a, r = grads[0][1][k], grads[1][1][k]
+        if float(r.abs().max()) == 0.0:
+            ok = float(a.abs().max()) < 1e-6
+            err = float(a.abs().max())
+        else:
+            err = rel_l2(a, r)
+            ok = err < tol
+        lines.append('%5s %-24s %.2e' % ('ok' if ok else 'FAIL', k, err))
+        if not ok:
+            bad.append(k)
+    print('\n' + '\n'.join(lines))
+    assert not bad, bad
+    check_dev()
