@@ -260,6 +260,29 @@ typedef struct {
 } sg_sdfnet_bwd_args;
 int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream);
 
+/* Data-parallel optimizer step as ONE kernel over NVLink peer memory (replaces nn.DataParallel's gradient reduction,
+ * train_hybrid_progressive_gan.py:62-71, + torch.optim.RMSprop/Adam .step(), train_wgan.py:45-46,70): every rank owns a shard of the flat
+ * arena and its optimizer state; in-barrier -> reduce its shard straight out of all peers' gradient arenas (float4 loads over NVLink) ->
+ * update -> store the new parameters into every peer's parameter arena -> out-barrier.  peer_grad / peer_param / peer_pad are HOST
+ * arrays of `world` device pointers into symmetric (peer-mapped) memory: gradient arenas, parameter arenas, and uint32 [2][world] signal
+ * pads (zero-initialised once).  sync = local uint32 [3] (zero-initialised once).  chunk = shard length (multiple of 4, chunk*world >= n);
+ * s1 / s2 hold the state of the LOCAL shard only.  kind 0 = RMSprop (beta1 = alpha), 1 = Adam (`step` = 1-based step count).
+ * Capturable; every rank must launch it in the same order. */
+typedef struct {
+  const void* const* peer_grad;
+  const void* const* peer_param;
+  const void* const* peer_pad;
+  int32_t rank, world;
+  int64_t n, chunk;
+  float* s1;
+  float* s2;
+  int32_t kind;
+  float lr, beta1, beta2, eps, clip, grad_scale;
+  int32_t step;
+  void* sync;
+} sg_dp_step_args;
+int sg_dp_step(const sg_dp_step_args* a, void* stream);
+
 /* ---- non-GEMM pieces of the hand-scheduled critic update (shapegan_b200/critic.py) ----
  * sg_gp_interp : out[b] = alpha[b] * real[b] + (1 - alpha[b]) * fake[b]          (train_hybrid_progressive_gan.py:103-105), m floats per sample
  * sg_gp_seed   : n_b = |g_b|_2 ; *gp_sum += weight (n_b - 1)^2 / B ; v_b = 2 weight (n_b - 1) / (B n_b) g_b   (:110-111 and its derivative w.r.t. g)

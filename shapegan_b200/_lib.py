@@ -56,6 +56,13 @@ class SgSdfnetBwdArgs(ctypes.Structure):
                 ('n', c_int64), ('gstash', c_void_p), ('gpoints', c_void_p), ('xyz_w', c_void_p)]
 
 
+class SgDpStepArgs(ctypes.Structure):
+    _fields_ = [('peer_grad', ctypes.POINTER(c_void_p)), ('peer_param', ctypes.POINTER(c_void_p)), ('peer_pad', ctypes.POINTER(c_void_p)),
+                ('rank', c_int32), ('world', c_int32), ('n', c_int64), ('chunk', c_int64), ('s1', c_void_p), ('s2', c_void_p),
+                ('kind', c_int32), ('lr', c_float), ('beta1', c_float), ('beta2', c_float), ('eps', c_float), ('clip', c_float),
+                ('grad_scale', c_float), ('step', c_int32), ('sync', c_void_p)]
+
+
 class SgMcArgs(ctypes.Structure):
     _fields_ = [('volume', c_void_p), ('nx', c_int32), ('ny', c_int32), ('nz', c_int32), ('level', c_float), ('spacing', c_float * 3),
                 ('block_sums', c_void_p), ('vbase', c_void_p), ('vertices', c_void_p), ('normals', c_void_p), ('faces', c_void_p)]
@@ -90,6 +97,7 @@ SYMBOLS = {
     'sg_sdfnet_fwd_layout': (c_int32, [ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
     'sg_sdfnet_bwd': (c_int32, [ctypes.POINTER(SgSdfnetBwdArgs), c_void_p]),
     'sg_sdfnet_infer': (c_int32, [ctypes.POINTER(SgSdfnetInferArgs), c_void_p]),
+    'sg_dp_step': (c_int32, [ctypes.POINTER(SgDpStepArgs), c_void_p]),
     'sg_mc_workspace_entries': (c_size_t, [c_int32, c_int32, c_int32]),
     'sg_mc_count': (c_int32, [ctypes.POINTER(SgMcArgs), c_void_p]),
     'sg_mc_emit': (c_int32, [ctypes.POINTER(SgMcArgs), c_void_p]),

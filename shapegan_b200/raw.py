@@ -376,6 +376,20 @@ def adam(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
     _call('sg_adam', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale)
 
 
+def dp_step(peers, n, s1, s2, kind, lr, step, grad_scale=1.0, clip=0.0, alpha=0.99, b1=0.9, b2=0.999, eps=1e-8):
+    """fused data-parallel optimizer step over peer memory (sg_dp_step); `peers` = train._PeerArenas"""
+    a = L.SgDpStepArgs()
+    a.peer_grad = ctypes.cast(peers.peer_grad, ctypes.POINTER(ctypes.c_void_p))
+    a.peer_param = ctypes.cast(peers.peer_param, ctypes.POINTER(ctypes.c_void_p))
+    a.peer_pad = ctypes.cast(peers.peer_pad, ctypes.POINTER(ctypes.c_void_p))
+    a.rank, a.world, a.n, a.chunk = peers.rank, peers.world, n, peers.chunk
+    a.s1, a.s2 = _p(s1), _p(s2)
+    a.kind = 0 if kind == 'rmsprop' else 1
+    a.lr, a.beta1, a.beta2, a.eps, a.clip, a.grad_scale = lr, (alpha if kind == 'rmsprop' else b1), b2, eps, clip, grad_scale
+    a.step, a.sync = step, _p(peers.sync)
+    L.check(L.lib().sg_dp_step(ctypes.byref(a), stream()), 'sg_dp_step')
+
+
 def clamp_(p, lo, hi):
     _call('sg_clamp', _p(p), p.numel(), lo, hi)
 

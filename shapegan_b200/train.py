@@ -29,8 +29,41 @@ def _fused_critic_enabled():
     return os.environ.get('SG_B200_NO_FUSED_CRITIC') != '1'
 
 
+def _fused_dp_enabled():
+    return os.environ.get('SG_B200_DP', 'fused') == 'fused'
+
+
+class _PeerArenas:
+    """Symmetric (peer-mapped) gradient / parameter arenas + signal pads of one FlatOptimizer for the fused data-parallel step
+    (csrc/sg_dp.cu): every rank can load every peer's gradients and store into every peer's parameters over NVLink."""
+
+    def __init__(self, n, dev, world, rank):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD
+        n_pad = raw.round_up(n, 4)
+        self.world, self.rank = world, rank
+        self.chunk = raw.round_up((n_pad + world - 1) // world, 4)
+        self.flat_full = symm.empty(n_pad, dtype=torch.float32, device=dev)
+        self.grad_full = symm.empty(n_pad, dtype=torch.float32, device=dev)
+        self.pads = symm.empty(max(2 * world, 32), dtype=torch.int32, device=dev)
+        self.flat_full.zero_(); self.grad_full.zero_(); self.pads.zero_()
+        hs = [symm.rendezvous(t, group) for t in (self.grad_full, self.flat_full, self.pads)]
+        self._handles = hs
+        mk = lambda h: (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(h.buffer_ptrs[r])) for r in range(world)])     # noqa: E731
+        self.peer_grad, self.peer_param, self.peer_pad = mk(hs[0]), mk(hs[1]), mk(hs[2])
+        self.sync = torch.zeros(4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier()                                   # every rank's pads are zero before anybody signals
+
+
 class FlatOptimizer:
-    """Flat-arena RMSprop / Adam with torch.optim default hyper-parameters (train_wgan.py:45-46, train_gan.py:28-31)."""
+    """Flat-arena RMSprop / Adam with torch.optim default hyper-parameters (train_wgan.py:45-46, train_gan.py:28-31).
+
+    world_size > 1: the step is ONE kernel over NVLink peer memory (sg_dp_step: reduce-scatter of the gradient arenas by peer loads,
+    the update of the rank's own shard -- optimizer state is sharded --, all-gather of the new parameters by peer stores) when the
+    arenas can live in symmetric memory; otherwise (SG_B200_DP=nccl, or no symmetric memory) one NCCL all-reduce + the fused update."""
 
     def __init__(self, params, kind, lr, clip=0.0, world_size=1):
         self.params = [p for p in params]
@@ -42,9 +75,23 @@ class FlatOptimizer:
         self.params = uniq
         self.kind, self.lr, self.clip, self.world = kind, lr, clip, world_size
         n = sum(p.numel() for p in self.params)
+        self.n = n
         dev = self.params[0].device
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.peers, self.dp_note = None, 'single'
+        if world_size > 1:
+            self.dp_note = 'nccl all-reduce + fused update'
+            if _fused_dp_enabled() and dev.type == 'cuda':
+                try:
+                    self.peers = _PeerArenas(n, dev, world_size, dist.get_rank())
+                    self.dp_note = 'sg_dp_step (peer-memory reduce-scatter + sharded update + all-gather, one kernel)'
+                except Exception as e:                    # no symmetric memory on this platform / build: NCCL path
+                    self.peers = None
+                    self.dp_note = 'nccl all-reduce + fused update (symmetric memory unavailable: %s)' % str(e).split('\n')[0][:80]
+        if self.peers is not None:
+            self.flat, self.grad = self.peers.flat_full[:n], self.peers.grad_full[:n]
+        else:
+            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
             k = p.numel()
@@ -52,8 +99,11 @@ class FlatOptimizer:
             p.data = self.flat[off:off + k].view_as(p.data)           # parameters become views of the arena
             p.grad = self.grad[off:off + k].view_as(p.data)           # autograd accumulates in place into the arena
             off += k
-        self.s1 = torch.zeros(n, dtype=torch.float32, device=dev)     # square_avg / exp_avg
-        self.s2 = torch.zeros(n, dtype=torch.float32, device=dev) if kind == 'adam' else None
+        if world_size > 1 and dev.type == 'cuda':
+            dist.broadcast(self.flat, 0)                              # replicas start from rank 0's parameters (what nn.DataParallel does every forward)
+        n_state = self.peers.chunk if self.peers is not None else n   # fused path: state of the local shard only
+        self.s1 = torch.zeros(n_state, dtype=torch.float32, device=dev)     # square_avg / exp_avg
+        self.s2 = torch.zeros(n_state, dtype=torch.float32, device=dev) if kind == 'adam' else None
         self.steps = 0
         from .ops import invalidate_weight_cache
         invalidate_weight_cache()
@@ -62,10 +112,14 @@ class FlatOptimizer:
         self.grad.zero_()
 
     def step(self):
-        if self.world > 1:
-            dist.all_reduce(self.grad)                                 # NCCL ring/NVLS over NVLink 5
         self.steps += 1
         scale = 1.0 / self.world
+        if self.peers is not None:
+            raw.dp_step(self.peers, self.n, self.s1, self.s2, self.kind, self.lr, self.steps, grad_scale=scale, clip=self.clip)
+            _bump_versions(self.params)
+            return
+        if self.world > 1:
+            dist.all_reduce(self.grad)                                 # NCCL ring/NVLS over NVLink 5
         if self.kind == 'rmsprop':
             raw.rmsprop(self.flat, self.grad, self.s1, self.lr, grad_scale=scale, clip=self.clip)
         else:
