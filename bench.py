@@ -419,6 +419,7 @@ def make_cnn_workload(kind, b, rank, world, dev, gp_fused=True):
     nec, written = gflop_per_sample(kind)
     w = Workload(kind, body, host, devt, d_loss, b * VOX, nec * b, written * b)
     w.keep = (gen, dis, step)
+    w.dp_note = (step.copt if kind != 'gan' else step.dopt).dp_note
     return w
 
 
@@ -446,6 +447,7 @@ def make_hybrid_workloads(b, rank, world, dev):
     wd = Workload('hybrid_d_update', d_body, host, devt, dl, b * 64 ** 3, d_nec * b)
     wg = Workload('hybrid_g_update', g_body, [host[1]], [devt[1]], gl, b * 64 ** 3, g_nec * b)
     wd.keep = wg.keep = (gen, dis, step)
+    wd.dp_note = wg.dp_note = step.dopt.dp_note
     return wd, wg
 
 
@@ -484,28 +486,28 @@ def measure(w, steps, warmup, world, flush, lib, no_graph=False, sampler=None):
     barrier(world)
     if sampler is not None:
         sampler.mark_begin()
-    total = 0.0
-    for _ in range(steps):
+    # per-iteration CUDA events, ONE host synchronisation at the end: the device queue stays full (no host jitter between iterations,
+    # which at N > 1 every collective would turn into a wait for the slowest rank); the L2 flush sits between the event pairs
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); run(); e1.record()
-        torch.cuda.synchronize()
-        total += e0.elapsed_time(e1)
+    torch.cuda.synchronize()
+    total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     barrier(world)
     ms = max_over_ranks(total / steps, world)
     barrier(world)
-    e2e = 0.0
-    for _ in range(steps):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for d, h in zip(w.dev, w.host):
             d.copy_(h, non_blocking=True)
         run()
         w.h_loss.copy_(w.d_loss, non_blocking=True)
         e1.record()
-        torch.cuda.synchronize()
-        e2e += e0.elapsed_time(e1)
+    torch.cuda.synchronize()
+    e2e = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     barrier(world)
     if sampler is not None:
         sampler.mark_end()
@@ -515,7 +517,7 @@ def measure(w, steps, warmup, world, flush, lib, no_graph=False, sampler=None):
     return {'ms_per_step': ms, 'value': world * w.units / (ms * 1e-3),
             'e2e': {'value': world * w.units / (e2e_ms * 1e-3), 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': int(sum(h.numel() * h.element_size() for h in w.host)), 'd2h_bytes_per_step': int(w.h_loss.numel() * 4)},
-            'launch': note, 'gpu_launches_per_step': int(launches), 'steps': steps,
+            'launch': note, 'gpu_launches_per_step': int(launches), 'steps': steps, 'data_parallel': getattr(w, 'dp_note', 'single'),
             'step_gflop_necessary': w.nec_gflop, 'step_gflop_as_written': w.written_gflop,
             'step_tflops': w.nec_gflop / ms, 'step_frac_of_sustained_peak': w.nec_gflop / ms / sus,
             'losses': [float(x) for x in w.h_loss]}
@@ -633,7 +635,7 @@ def main():
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'bf16x3(fp32x)', 'data': 'synthetic',
         'config': {'workload': workload_name(args.workload, b),
-                   'global_batch': world * b, 'parallelism': 'dp%d' % world, 'launch': res['launch'],
+                   'global_batch': world * b, 'parallelism': 'dp%d' % world, 'launch': res['launch'], 'data_parallel': res['data_parallel'],
                    'l2': 'flushed (256 MiB memset) between timed iterations',
                    'step_gflop_necessary': res['step_gflop_necessary'], 'step_gflop_as_written': res['step_gflop_as_written'],
                    'step_tflops': res['step_tflops'], 'step_frac_of_sustained_peak': res['step_frac_of_sustained_peak'],
