@@ -291,6 +291,23 @@ int sg_gp_interp(const float* real, const float* fake, const float* alpha, float
 int sg_gp_seed(const float* g, float* v, int b, int64_t m, float weight, double* gp_sum, void* stream);
 int sg_critic_loss(const float* scores, int b, const double* gp_sum, float* out4, void* stream);
 
+/* ---- point-set GAN path (model/point_sdf_net.py): everything that is not a Linear layer; plane tensors [P][rows][C], C % 8 == 0 ----
+ * sg_ln_act_fwd/bwd : y = act(LayerNorm_C(x) gamma + beta) (eps inside the root, biased variance), stats = fp32 [rows][2] (mean, rstd);
+ *                     bwd also returns dbeta / dgamma (workspace: >= 2*C floats per block, up to 296 blocks; deterministic)
+ * sg_rows_add_vec   : y[row] = x[row] + v[row / seg_len]   (z_lin(z).unsqueeze(1) + x, :105-109); sg_segment_colsum = its backward w.r.t. v
+ * sg_segmax_fwd     : out[s] = max over the seg_len rows of segment s, arg[s][c] = first arg-max row (x.max(dim=-2)[0], :40-41)
+ * sg_segmax_move    : gather = 0: big[s*seg_len + arg[s][c]][c] = small[s][c] (big pre-zeroed) ; gather = 1: the reverse */
+int sg_ln_act_fwd(const void* x, int64_t x_ps, void* y, int64_t y_ps, int planes, int64_t rows, int c, const float* gamma, const float* beta,
+                  float eps, int act, float* stats, void* stream);
+int sg_ln_act_bwd(const void* gy, int64_t gy_ps, const void* y, int64_t y_ps, const void* x, int64_t x_ps, void* gx, int64_t gx_ps, int planes,
+                  int64_t rows, int c, const float* gamma, int act, const float* stats, float* gbeta, float* ggamma, float* workspace,
+                  int64_t workspace_floats, void* stream);
+int sg_rows_add_vec(const void* x, int64_t x_ps, const float* v, void* y, int64_t y_ps, int planes, int64_t rows, int c, int64_t seg_len, void* stream);
+int sg_segment_colsum(const void* x, int64_t x_ps, int planes, int segs, int c, int64_t seg_len, float* out, void* stream);
+int sg_segmax_fwd(const void* x, int64_t x_ps, int planes, int segs, int c, int64_t seg_len, void* out, int64_t out_ps, int32_t* arg, void* stream);
+int sg_segmax_move(void* big, int64_t big_ps, void* small, int64_t small_ps, int planes, int segs, int c, int64_t seg_len, const int32_t* arg,
+                   int gather, void* stream);
+
 /* ---- SDFNet inference consumers / voxel data path ---- */
 /* Cells s = (ix*r + iy)*r + iz of the util.get_voxel_coordinates(r) grid (util.py:60-74) with |p| < radius, the sphere mask of
  * SDFVoxelizationHelperData (model/sdf_net.py:12-14), evaluated in numpy's float32 arithmetic operation by operation (bit-exact set).

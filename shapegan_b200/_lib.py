@@ -126,6 +126,12 @@ SYMBOLS = {
     'sg_clamp': 'plffp',
     'sg_sum_f32': 'plpp',
     'sg_l1_loss_grad': 'ppplpp',
+    'sg_ln_act_fwd': 'plplilippfipp',
+    'sg_ln_act_bwd': 'plplplplilipipppplp',
+    'sg_rows_add_vec': 'plpplililp',
+    'sg_segment_colsum': 'pliiilpp',
+    'sg_segmax_fwd': 'pliiilplpp',
+    'sg_segmax_move': 'plpliiilpip',
     'sg_gp_interp': 'ppppilp',
     'sg_gp_seed': 'ppilfpp',
     'sg_critic_loss': 'pippp',

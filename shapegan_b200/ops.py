@@ -304,11 +304,15 @@ class DenseOp(LinOp):
     4^3 grid (autoencoder.py:28: t = position, c = cin) and the NCDHW-flatten + Linear head of progressive_gan.py:27-28
     (t = position, c = channel).  Input/output are plane tensors [P, rows, K] / [P, rows, N]."""
 
-    def __init__(self, n1, n0, s_n1, s_n0, t, c, s_t, s_c, tag):
+    def __init__(self, n1, n0, s_n1, s_n0, t, c, s_t, s_c, tag, c_valid=None):
+        """c_valid < c: the input rows carry c physical columns of which only the first c_valid exist in the weight (zero padding of
+        narrow inputs such as xyz / xyz+dist up to the kernels' K granularity); only with t == 1 and n1 == 1"""
         self.n1, self.n0, self.s_n1, self.s_n0 = n1, n0, s_n1, s_n0
         self.t, self.c, self.s_t, self.s_c = t, c, s_t, s_c
         self.n, self.k = n1 * n0, t * c
         self.tag = tag
+        self.c_valid = c if c_valid is None else c_valid
+        assert self.c_valid == c or (t == 1 and n1 == 1)
         assert self.n % 8 == 0 and self.k % 8 == 0, 'DenseOp needs N, K multiples of 8'
         assert n1 == 1 or t == 1, 'DenseOp: only one side may be two-level'
 
@@ -316,7 +320,7 @@ class DenseOp(LinOp):
         p, rows = x.shape[0], x.shape[1]
         y = out if out is not None else _new((rows, self.n), x.device)
         img = PACK_CACHE.get(w, self.tag + '_f', p, lambda tt, pl: raw.pack_b(
-            tt, pl, self.n, r64(self.k), self.t, self.c, self.c, s_n0=self.s_n0, s_tap=self.s_t, s_c=self.s_c,
+            tt, pl, self.n, r64(self.k), self.t, self.c, self.c_valid, s_n0=self.s_n0, s_tap=self.s_t, s_c=self.s_c,
             n0_count=self.n0, s_n1=self.s_n1))
         raw.igemm(L.MODE_DENSE, p, x, (1, 1, 1, 1, self.k), rows, r64(self.k), img, self.n, y, self.n, bias=bias, act=act,
                   bias_mod=self.n0 if (self.n1 > 1 and bias is not None) else 0, mask=mask, mask_act=mask_act)
@@ -325,10 +329,12 @@ class DenseOp(LinOp):
     def tr(self, g, w, mask=None, mask_act=ACT_NONE):
         p, rows = g.shape[0], g.shape[1]
         gx = _new((rows, self.k), g.device)
+        kv = self.c_valid if self.c_valid != self.c else self.k         # rows >= c_valid of the image are zero: those gx columns come out 0
         img = PACK_CACHE.get(w, self.tag + '_t', p, lambda tt, pl: raw.pack_b(
-            tt, pl, self.k, r64(self.n), self.n1, self.n0, self.n0, s_n0=self.s_c, s_tap=self.s_n1, s_c=self.s_n0,
-            n0_count=self.c, s_n1=self.s_t))
-        raw.igemm(L.MODE_DENSE, p, g, (1, 1, 1, 1, self.n), rows, r64(self.n), img, self.k, gx, self.k, mask=mask, mask_act=mask_act)
+            tt, pl, kv, r64(self.n), self.n1, self.n0, self.n0, s_n0=self.s_c, s_tap=self.s_n1, s_c=self.s_n0,
+            n0_count=self.c, s_n1=self.s_t, n_pad=raw.round_up(self.k, 16)))
+        raw.igemm(L.MODE_DENSE, p, g, (1, 1, 1, 1, self.n), rows, r64(self.n), img, self.k, gx, self.k, mask=mask, mask_act=mask_act,
+                  n_pad=raw.round_up(self.k, 16))
         return gx
 
     def wgrad(self, x, g, w_shape, into=None):
@@ -337,7 +343,7 @@ class DenseOp(LinOp):
         acc = into is not None
         if self.n1 == 1:      # A = g (one-level n0), B = x (t, c)
             raw.wgrad(L.MODE_DENSE, p, g, self.n, x, (1, 1, 1, 1, self.k), rows, gw, sm=self.s_n0, st=self.s_t, sc=self.s_c,
-                      m_valid=self.n, taps=self.t, cb=self.c, accumulate=acc)
+                      m_valid=self.n, taps=self.t, cb=self.c, accumulate=acc, c_valid=self.c_valid if self.c_valid != self.c else 0)
         else:                 # A = x (one-level c), B = g (n1, n0)
             raw.wgrad(L.MODE_DENSE, p, x, self.k, g, (1, 1, 1, 1, self.n), rows, gw, sm=self.s_c, st=self.s_n1, sc=self.s_n0,
                       m_valid=self.k, taps=self.n1, cb=self.n0, accumulate=acc)

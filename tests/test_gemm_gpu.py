@@ -137,8 +137,9 @@ def test_halo_variant(mode, b, cin, cout, mt, monkeypatch):
     L, raw = _imports()
     bias = rnd((cout,), 3)
     outs = []
-    for no_halo in ('0', '1'):
+    for no_halo, no_pair in (('0', '0'), ('0', '1'), ('1', '1')):       # CTA-pair halo kernel | single-CTA halo kernel | plain kernel
         monkeypatch.setenv('SG_B200_NO_HALO', no_halo)
+        monkeypatch.setenv('SG_B200_NO_PAIR', no_pair)
         if mode == 'conv':
             r = 16
             x = rnd((b, r, r, r, cin), 1)
@@ -157,9 +158,11 @@ def test_halo_variant(mode, b, cin, cout, mt, monkeypatch):
                       out_kind=L.OUT_F32, bias=bias, out_dims=(16, 16, 16), mt=mt)
             ref = F.conv_transpose3d(q(x, 1).permute(0, 4, 1, 2, 3), q(w, 1), bias.double(), stride=2, padding=1)
             ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, cout)
-        report('halo=%s %s mt%d %s' % ('off' if no_halo == '1' else 'on', mode, mt, (b, cin, cout)), out, ref, TOL_F32)
+        report('halo=%s pair=%s %s mt%d %s' % ('off' if no_halo == '1' else 'on', 'off' if no_pair == '1' else 'on', mode, mt, (b, cin, cout)),
+               out, ref, TOL_F32)
         outs.append(out.clone())
-    assert (outs[0] - outs[1]).abs().max().item() < 1e-3 * max(1.0, outs[1].abs().max().item())
+    for o in outs[:2]:
+        assert (o - outs[2]).abs().max().item() < 1e-3 * max(1.0, outs[2].abs().max().item())
     check_error_word()
 
 

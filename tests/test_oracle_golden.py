@@ -205,3 +205,37 @@ def test_render_oracle_pinned_to_chairs_golden():
     # ingest == datasets.py:16-23
     raw = np.array([0.3, -0.2, 0.05, 0.1], dtype=np.float32)
     assert torch.equal(RR.ingest(raw), torch.tensor([1.0, -1.0, np.float32(0.05) / np.float32(0.1), 1.0]))
+
+
+def test_point_gan_oracle_pinned_to_reference_golden():
+    """oracle/ref_points.py against the golden of the unmodified model/point_sdf_net.py + train_point_gan.py:52-87"""
+    from oracle import ref_points as RP
+    g = load_golden('point_gan')
+    shapes_g = {'lins.%d.weight' % i: s for i, s in enumerate([(256, 3), (256, 256), (256, 256), (256, 256), (256, 259), (256, 256), (256, 256), (1, 256)])}
+    gsd, dsd = {}, {}
+    # rebuild the seeded state dicts in the reference modules' state_dict() ORDER
+    order_g = []
+    for i in range(8):
+        order_g += [('lins.%d.weight' % i, shapes_g['lins.%d.weight' % i]), ('lins.%d.bias' % i, (shapes_g['lins.%d.weight' % i][0],))]
+    for i in range(8):
+        c = 1 if i == 7 else 256
+        order_g += [('norms.%d.weight' % i, (c,)), ('norms.%d.bias' % i, (c,))]
+    order_g += [('z_lin1.weight', (256, 128)), ('z_lin1.bias', (256,)), ('z_lin2.weight', (256, 128)), ('z_lin2.bias', (256,))]
+    gsd = R.seeded_state_dict(dict(order_g), int(g['seed_gen']))
+    order_d = []
+    for i, (a, b) in zip((0, 2, 4, 6), ((4, 64), (64, 128), (128, 256), (256, 512))):
+        order_d += [('nn1.%d.weight' % i, (b, a)), ('nn1.%d.bias' % i, (b,))]
+    for i, (a, b) in zip((0, 2, 4), ((512, 256), (256, 128), (128, 1))):
+        order_d += [('nn2.%d.weight' % i, (b, a)), ('nn2.%d.bias' % i, (b,))]
+    dsd = R.seeded_state_dict(dict(order_d), int(g['seed_dis']))
+    pos, dist, alpha = (torch.from_numpy(g[k]) for k in ('pos', 'dist', 'alpha'))
+    fake = RP.sdf_generator_forward(gsd, pos, torch.from_numpy(g['z_dis']))
+    assert rel_l2(fake, g['fake']) < TOL
+    assert rel_l2(RP.pointnet_forward(dsd, pos, dist), g['out_real']) < TOL
+    for v in dsd.values():
+        v.requires_grad_(True)
+    total, d_loss, gp = RP.critic_loss_with_gp(dsd, pos, dist, fake.detach(), alpha)
+    assert abs(d_loss.item() - float(g['d_loss'])) < 1e-5 and abs(gp.item() - float(g['gp'])) < 1e-4 * max(1.0, float(g['gp']))
+    total.backward()
+    for k, v in dsd.items():
+        check_digest(g, 'dis_grad.' + k, v.grad, 2e-4, k, atol=1e-7)
