@@ -175,6 +175,8 @@ class CriticUpdate:
         hw = head['w']
         if hw.grad is None:
             hw.grad = torch.zeros_like(hw)
+        if head['b'] is not None and head['b'].grad is None:
+            head['b'].grad = torch.zeros_like(head['b'])          # d loss / d b_head = sum of the seeds of the Wasserstein rows = 0
         _, sums = raw.rowdot_bwd(seeds, scores, L.ACT_NONE, hf, head['c'], hw.detach(), False, True, planes, n, head['wc'], head['s_t'], head['s_c'])
         raw.emit_sums(sums, hw.grad, head['c'], accumulate=True, wc=head['wc'] if head['wc'] > 0 else 0, s_t=head['s_t'], s_c=head['s_c'])
         return out4

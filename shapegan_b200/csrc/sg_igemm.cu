@@ -50,6 +50,7 @@ struct IgemmP {
   CUtensorMap tmA2[2];   // second DENSE source
   // halo variant (sg_igemm_halo_kernel): one strided box of (8+1) x 8 x (2 mt + 1) grid points serves the 4 taps (qz, qx)
   int halo; unsigned blk_bytes; int b_stages;
+  int pair;              // sg_igemm_halo2_kernel: CTA pairs, tcgen05.mma.cta_group::2 (each CTA: its own 128-row tiles + half of every weight tile)
   CUtensorMap tmH;
 };
 
@@ -87,6 +88,7 @@ struct EpiP {   // the fields the epilogue needs, copied ONCE into registers: th
                 // reference here, and every p.field access would otherwise be a generic load with a long-scoreboard stall
   int mode, planes, n_valid, bn, mt, ksplit, m_tiles, n_tiles, bias_mod, act, mask_act, out_kind, out_ld, oD, oH, oW, aD, aH, aW, acc_bufs, acc_slot;
   long long rows, work_total, out_ps, ks_stride;
+  int pair;               // CTA-pair kernel: work items are pairs of M tiles, this CTA owns tile 2*mtile + cluster rank
   const float* bias; const bf16* mask; char* out; int* err;
 };
 
@@ -96,7 +98,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
   p.mode = gp.mode; p.planes = gp.planes; p.n_valid = gp.n_valid; p.bn = gp.bn; p.mt = gp.mt; p.ksplit = gp.ksplit;
   p.m_tiles = gp.m_tiles; p.n_tiles = gp.n_tiles; p.bias_mod = gp.bias_mod; p.act = gp.act; p.mask_act = gp.mask_act;
   p.out_kind = gp.out_kind; p.out_ld = gp.out_ld; p.oD = gp.oD; p.oH = gp.oH; p.oW = gp.oW; p.aD = gp.aD; p.aH = gp.aH; p.aW = gp.aW;
-  p.acc_bufs = gp.acc_bufs; p.acc_slot = gp.acc_slot; p.rows = gp.rows; p.work_total = gp.work_total; p.out_ps = gp.out_ps; p.ks_stride = gp.ks_stride;
+  p.pair = gp.pair; p.acc_bufs = gp.acc_bufs; p.acc_slot = gp.acc_slot; p.rows = gp.rows; p.work_total = gp.work_total; p.out_ps = gp.out_ps; p.ks_stride = gp.ks_stride;
   p.bias = gp.bias; p.mask = gp.mask; p.out = gp.out; p.err = gp.err;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -104,9 +106,15 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
   const int etid = threadIdx.x - 5 * 32;  // 0..127 among the epilogue threads
   float* sbias = hdr->sbias;
   int it = 0, staged_nt = -1;
-  for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
+  const uint32_t crank = p.pair ? cluster_ctarank() : 0u;
+  const long long w0 = p.pair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long wstep = p.pair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  // pair kernel: the accumulator-drained signal goes to the LEADER's barrier (its MMA thread feeds both CTAs' accumulators)
+  const uint32_t accempty_addr[2] = {p.pair ? mapa_u32(smem_u32(&hdr->accempty[0]), 0) : 0u, p.pair ? mapa_u32(smem_u32(&hdr->accempty[1]), 0) : 0u};
+  for (long long w = w0; w < p.work_total; w += wstep, ++it) {
     int cls, nt, mtile, ks;
     decode_work(p, w, cls, nt, mtile, ks);
+    if (p.pair) mtile = mtile * 2 + (int)crank;
     const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
     const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
     const bool add_bias = (p.bias != nullptr) && (ks == 0);
@@ -119,7 +127,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
       asm volatile("bar.sync 1, 128;" ::: "memory");
       staged_nt = nt;
     }
-    mbar_wait(&hdr->accfull[ab], aph, p.err);
+    if (p.pair) mbar_wait_cluster(&hdr->accfull[ab], aph, p.err); else mbar_wait(&hdr->accfull[ab], aph, p.err);
     tc_fence_after();
     const bool tile_full = (nt * p.bn + p.bn <= p.n_valid);
     const bool fast = tile_full && (p.bn & 31) == 0 &&
@@ -225,7 +233,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
       }
     }
     tc_fence_before();
-    mbar_arrive(&hdr->accempty[ab]);
+    if (p.pair) mbar_arrive_cluster(accempty_addr[ab]); else mbar_arrive(&hdr->accempty[ab]);
   }
 }
 
@@ -777,6 +785,168 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const _
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ================================================================================================ halo variant on CTA PAIRS
+// Same K sequence and halo views as sg_igemm_halo_kernel, on a 2-CTA cluster with tcgen05.mma.cta_group::2: every MMA spans 256 rows
+// (this CTA's 128-row sub-tile + the peer's) and the weight tile is SPLIT between the two CTAs -- each stages only bn / 2 of its rows.
+// What this buys: the single-CTA M128 x N128 x K16 MMA reads 8 KB of shared-memory operands for 64 clocks of math and is paced by
+// those reads (~108 clk measured); in the pair each SM reads its 4 KB A slice + 2 KB B slice for the same math.
+//   leader (cluster rank 0): its MMA thread issues for both CTAs; its barriers collect the pair's arrivals
+//     blk_full[i]   count 1 + transaction bytes of BOTH CTAs' halo blocks (peer's TMA reports to the leader: .cta_group::2 form)
+//     full[s]       2 x 96 weight-loader threads (the peer's arrive through shared::cluster)
+//     accempty[ab]  2 x 128 epilogue threads
+//   both CTAs: blk_empty / empty / accfull are signalled by tcgen05.commit ... multicast::cluster to the same offset in each CTA.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo2_kernel(const __grid_constant__ IgemmP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+  uint8_t* blk0 = smem + kSmemHeader;
+  uint8_t* bst0 = blk0 + 2 * (size_t)p.blk_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int SB = p.b_stages;
+  const uint32_t b_half_bytes = (uint32_t)(p.bn / 2) * 128u;      // this CTA's half of a weight tile
+  const int cchunks = p.aC >> 6;
+  const int ngroups = (p.mode == SG_MODE_CONV) ? 16 : 2;
+  const long long w0 = blockIdx.x >> 1, wstep = gridDim.x >> 1;
+  if (tid == 0) {
+    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], 2 * kBLoaderThreads); mbar_init(&hdr->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 256);
+      mbar_init(&hdr->blk_full[i], 1); mbar_init(&hdr->blk_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc2(&hdr->tmem_base, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0) atomicExch(p.err, kErrSmemAlign);
+    __trap();
+  }
+
+  if (warp == 0) {
+    // ================================================================ TMA producer: this CTA's halo blocks; bytes reported to the leader
+    if (elect_one()) {
+      tma_prefetch_desc(&p.tmH);
+      int bi = 0; uint32_t bph = 0;
+      const int lgz = 31 - __clz(max(p.gz, 1));
+      for (long long w = w0; w < p.work_total; w += wstep) {
+        int cls, nt, mtile, ks;
+        decode_work(p, w, cls, nt, mtile, ks);
+        mtile = mtile * 2 + (int)crank;
+        const int pd = (cls >> 2) & 1, phh = (cls >> 1) & 1, pw = cls & 1;
+        const uint32_t row0 = (uint32_t)(mtile * p.mt) * kTileRows;
+        const int z0 = (int)((row0 >> 6) & (uint32_t)(p.gz - 1)), n0 = (int)(row0 >> (6 + lgz));
+        for (int grp = 0; grp < ngroups; ++grp) {
+          int x, y, z;
+          if (p.mode == SG_MODE_CONV) {
+            const int kh = grp >> 2, pz = (grp >> 1) & 1, px = grp & 1;
+            x = -1 + px; y = -1 + kh; z = 2 * z0 - 1 + pz;
+          } else {
+            const int th = grp;
+            x = pw ? 0 : -1; y = phh ? 1 - th : -th; z = z0 + (pd ? 0 : -1);
+          }
+          for (int cc = 0; cc < cchunks; ++cc) {
+            mbar_wait_cluster(&hdr->blk_empty[bi], bph ^ 1, p.err);
+            if (leader) mbar_arrive_expect_tx(&hdr->blk_full[bi], 2u * p.blk_bytes);
+            tma_load_5d_2sm(smem_u32(blk0 + (size_t)bi * p.blk_bytes), &p.tmH, cc * 64, x, y, z, n0, &hdr->blk_full[bi]);
+            if (++bi == 2) { bi = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================================================================ weight-tile loaders: this CTA's HALF (rows crank * bn/2 ...) of every tap's tile
+    const int bt = tid - 32;
+    int s = 0; uint32_t ph = 0;
+    int pending = 0, oldest = 0;
+    const uint32_t pieces = (uint32_t)(p.bn / 2) * 8u;
+    uint32_t full_addr[kMaxStages];
+    for (int i = 0; i < kMaxStages; ++i) full_addr[i] = mapa_u32(smem_u32(&hdr->full[i]), 0);
+    for (long long w = w0; w < p.work_total; w += wstep) {
+      int cls, nt, mtile, ks;
+      decode_work(p, w, cls, nt, mtile, ks);
+      const char* bcls = p.b + ((size_t)cls * p.kchunks * p.n_pad + (size_t)nt * p.bn + (size_t)crank * (p.bn / 2)) * 128;
+      for (int grp = 0; grp < ngroups; ++grp)
+        for (int cc = 0; cc < cchunks; ++cc)
+          for (int t4 = 0; t4 < 4; ++t4) {
+            const int kc = halo_tap(p, grp, t4) * cchunks + cc;
+            const char* bsrc = bcls + (size_t)kc * p.n_pad * 128;
+            mbar_wait_cluster(&hdr->empty[s], ph ^ 1, p.err);
+            const uint32_t b_dst = smem_u32(bst0 + (size_t)s * b_half_bytes);
+            for (uint32_t i = (uint32_t)bt; i < pieces; i += kBLoaderThreads) cp_async16(b_dst + i * 16u, bsrc + (size_t)i * 16u, 16u);
+            cp_async_commit();
+            if (++pending > 1) {
+              cp_async_wait<1>(); fence_proxy_async(); mbar_arrive_cluster(full_addr[oldest]);
+              if (++oldest == SB) oldest = 0;
+              --pending;
+            }
+            if (++s == SB) { s = 0; ph ^= 1; }
+          }
+    }
+    while (pending > 0) {
+      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive_cluster(full_addr[oldest]);
+      if (++oldest == SB) oldest = 0;
+      --pending;
+    }
+  } else if (warp == 4) {
+    // ================================================================ MMA issuer: one elected thread of the LEADER CTA
+    if (leader && elect_one()) {
+      const uint32_t idesc = umma_idesc(256, p.bn, false, false);
+      int s = 0; uint32_t ph = 0; int it = 0;
+      int bi = 0; uint32_t bph = 0;
+      for (long long w = w0; w < p.work_total; w += wstep, ++it) {
+        const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
+        const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
+        mbar_wait_cluster(&hdr->accempty[ab], aph ^ 1, p.err);
+        tc_fence_after();
+        bool first = true;
+        for (int grp = 0; grp < ngroups; ++grp)
+          for (int cc = 0; cc < cchunks; ++cc) {
+            mbar_wait_cluster(&hdr->blk_full[bi], bph, p.err);
+            const uint32_t blk = smem_u32(blk0 + (size_t)bi * p.blk_bytes);
+            for (int t4 = 0; t4 < 4; ++t4) {
+              const int qz = t4 >> 1, qx = t4 & 1;
+              mbar_wait_cluster(&hdr->full[s], ph, p.err);
+              tc_fence_after();
+              const uint32_t b_base = smem_u32(bst0 + (size_t)s * b_half_bytes);
+              for (int sub = 0; sub < p.mt; ++sub) {
+                const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
+                const uint32_t a_view = blk + (uint32_t)(((sub * 2 + qz) * 8) * 9 + qx) * 128u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t da = umma_desc(a_view + kk * 32, 16, 9 * 128);
+                  const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
+                  umma2_bf16(d_addr, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              umma2_commit(&hdr->empty[s]);
+              if (++s == SB) { s = 0; ph ^= 1; }
+            }
+            umma2_commit(&hdr->blk_empty[bi]);
+            if (++bi == 2) { bi = 0; bph ^= 1; }
+          }
+        umma2_commit(&hdr->accfull[ab]);
+      }
+    }
+    __syncwarp();
+  } else {
+    switch (p.act) {
+      case ACT_NONE: epilogue_role<ACT_NONE>(p, hdr, tmem_base, p.kchunks); break;
+      case ACT_LRELU: epilogue_role<ACT_LRELU>(p, hdr, tmem_base, p.kchunks); break;
+      case ACT_RELU: epilogue_role<ACT_RELU>(p, hdr, tmem_base, p.kchunks); break;
+      default: epilogue_role<-1>(p, hdr, tmem_base, p.kchunks); break;
+    }
+  }
+  // neither CTA may leave while the other can still touch its shared memory, barriers or tensor memory
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
+}
+
 // ================================================================================================ host launcher
 static int igemm_validate(const sg_igemm_args* a) {
   if (!a) return sg_fail(-1, "sg_igemm: null args");
@@ -901,6 +1071,15 @@ static int igemm_tiles(const sg_igemm_args* a, bool ws_ok, TileCfg* t) {
     if (ksplit <= 0 && ws_ok && !no_split && a->out_kind != SG_OUT_F32_ATOMIC && items * 2 <= sms && kchunks >= 32 && (bn & 31) == 0) {
       int ks = (int)(sms / items);
       while (ks > 1 && kchunks / ks < 16) --ks;
+      if (ks > 1) { ksplit = ks; auto_split = true; }
+    }
+    // fp32x (hi/lo planes): the tensor core adds every K = 16 step into its fp32 accumulator with truncation (a BIASED ~2^-24 |acc| per
+    // step: 5e-5 of the output at K = 16384, profiles/r02b_parity_errors.txt) and the gradients that follow amplify a bias through
+    // their cancelling sums.  The parity mode therefore accumulates at most 8 chunks (K = 512) in TMEM and adds the chunk results in
+    // fp32 round-to-nearest (partial slabs + finish kernel): the same machinery as split-K.
+    if (ksplit <= 0 && ws_ok && !no_split && !auto_split && a->planes == 2 && a->out_kind != SG_OUT_F32_ATOMIC && kchunks > 8) {
+      int ks = std::min((kchunks + 7) / 8, 64);
+      while (ks > 1 && (size_t)ks * (size_t)t->out_rows * (size_t)a->n_pad * sizeof(float) > ((size_t)512 << 20)) ks = (ks + 1) / 2;
       if (ks > 1) { ksplit = ks; auto_split = true; }
     }
     // not enough work for the machine: narrow the N tile (keeps tensor throughput, multiplies CTAs)
@@ -1057,6 +1236,32 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
       const long long room = 227LL * 1024 - kSmemHeader - 2LL * p.blk_bytes;
       p.b_stages = (int)std::min<long long>(kMaxStages, room / b_tile);
       if (p.b_stages >= 3 && tma_make_map(&p.tmH, a->a.ptr, 5, dims, str, box, es)) p.halo = 1;
+    }
+  }
+  // CTA-pair variant of the halo kernel: an even number of M tiles per (class, N tile), whole pairs inside one sample's z range
+  if (p.halo) {
+    const char* no_pair = getenv("SG_B200_NO_PAIR");
+    const long long pair_tiles = p.m_tiles;
+    if (!(no_pair && no_pair[0] == '1') && (pair_tiles & 1) == 0 && (bn & 31) == 0 && bn >= 32 && p.gz % (4 * mt) == 0 && a->mask == nullptr) {
+      IgemmP q = p;
+      q.pair = 1;
+      q.m_tiles = p.m_tiles / 2;
+      q.work_total = (long long)q.classes * q.n_tiles * q.m_tiles;
+      const long long room = 227LL * 1024 - kSmemHeader - 2LL * q.blk_bytes;
+      q.b_stages = (int)std::min<long long>(kMaxStages, room / ((long long)(bn / 2) * 128));
+      const size_t psmem = kSmemHeader + 2 * (size_t)q.blk_bytes + (size_t)q.b_stages * (size_t)(bn / 2) * 128;
+      static bool pattr_set = false;
+      if (!pattr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sg_igemm_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+        pattr_set = true;
+      }
+      const int clusters = (int)std::min<long long>(q.work_total, sms / 2);
+      sg_igemm_halo2_kernel<<<2 * clusters, kIgemmThreads, psmem, (cudaStream_t)stream>>>(q);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+      sg_count_launch();
+      return 0;
     }
   }
   if (p.halo) {

@@ -61,6 +61,14 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"((uint32_t)__cvta_generic_to_shared(bar))
       : "memory");
 }
+// CTA-pair form: the transaction bytes are reported to the mbarrier at the same offset in the pair's LEADER CTA (rank 0)
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(bar) & 0xFEFFFFFFu;      // clear the peer bit: CTA 0's window
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(mbar)
+      : "memory");
+}
 // shared -> global tile store (bulk async-group completion): the box is read from 128B-swizzled shared memory
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(m), "r"(c0), "r"(c1), "r"(c2),

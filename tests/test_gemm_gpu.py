@@ -271,8 +271,8 @@ def test_splitk_partial_slabs(mode, b, r, cin, cout, ks, planes, monkeypatch):
                   mask_act=L.ACT_LRELU, out_dims=od, ksplit=ks if split else 0)
         outs.append((raw.from_planes(y), L.lib().sg_launch_count() - launches0))
     monkeypatch.delenv('SG_B200_NO_SPLITK')
-    assert outs[0][1] == 2 and outs[1][1] == 1, 'expected main + finish kernel vs a single launch, got %s' % ([o[1] for o in outs],)
-    report('splitk %s p%d ks%d' % (mode, planes, ks), outs[0][0], outs[1][0], 4e-3 if planes == 1 else 2e-5)
+    assert outs[0][1] == 2 and outs[1][1] == 1, 'expected main + finish kernel vs a single launch, got %s' % ([o[1] for o in outs],)      # SG_B200_NO_SPLITK also switches the fp32x K chunking off
+    report('splitk %s p%d ks%d' % (mode, planes, ks), outs[0][0], outs[1][0], 4e-3 if planes == 1 else 5e-5)
     check_error_word()
 
 

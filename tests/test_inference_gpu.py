@@ -75,6 +75,9 @@ def test_get_voxels_fused(r, sphere_only):
 
 
 def test_normals_against_oracle_autograd():
+    """d sdf / d xyz out of the fused backward chain vs autograd through the CPU oracle.  Compared where the gradient means something:
+    the SDF is clamped to +-0.1 in training, far from the surface it is flat and its 'normal' is the direction of rounding noise in
+    the reference as well."""
     net, sd, z = chairs()
     g = torch.Generator().manual_seed(5)
     n = 128 * 37 + 5
@@ -84,8 +87,18 @@ def test_normals_against_oracle_autograd():
     normals = net.get_normals(z.cuda(), p)
     assert p.requires_grad and p.grad is normals                 # the reference's side effects on the caller's tensor (:121,:124)
     assert torch.allclose(normals.norm(dim=1), torch.ones(n, device='cuda'), atol=1e-4)
-    cos = (normals.cpu() * n_ref).sum(1)
-    assert cos.mean().item() > 0.999 and (cos > 0.99).float().mean().item() > 0.995, (cos.mean().item(), (cos > 0.99).float().mean().item())
+    near = sdf_ref.abs() < 0.05
+    assert near.sum().item() > 300
+    cos = (normals.cpu() * n_ref).sum(1)[near]
+    assert cos.mean().item() > 0.998 and (cos > 0.99).float().mean().item() > 0.98, (cos.mean().item(), (cos > 0.99).float().mean().item())
+    # the un-normalised gradient itself
+    from shapegan_b200 import sdf_ops
+    with torch.no_grad():
+        sdf_dev, grad_dev = sdf_ops.normals_single_latent(net._params(), z.cuda(), pts.cuda(), normalize=False)
+    pr = pts.clone().requires_grad_(True)
+    R.sdfnet_forward(sd, pr, z.reshape(1, -1).repeat(n, 1)).sum().backward()
+    assert rel_l2(sdf_dev, sdf_ref) < 6e-3
+    assert rel_l2(grad_dev.cpu()[near], pr.grad[near]) < 3e-2
     # no parameter gradients are produced on this path
     assert all(q.grad is None for q in net.parameters())
 
@@ -93,11 +106,11 @@ def test_normals_against_oracle_autograd():
 def test_surface_points_land_on_the_surface():
     net, sd, z = chairs()
     torch.manual_seed(0)
-    pts, normals = net.get_surface_points(z.cuda(), sample_size=20000, return_normals=True)
-    assert pts.shape[0] > 1000 and pts.shape == normals.shape
+    pts, normals = net.get_surface_points(z.cuda(), sample_size=40000, sdf_cutoff=0.02, return_normals=True)
+    assert pts.shape[0] > 500 and pts.shape == normals.shape
     with torch.no_grad():
         d = R.sdfnet_forward(sd, pts.cpu(), z.reshape(1, -1).repeat(pts.shape[0], 1))
-    assert d.abs().median().item() < 5e-3                        # one projection step along the normal (:141)
+    assert d.abs().median().item() < 5e-3                        # one projection step along the normal (:141) from within 0.02 of the surface
 
 
 def _rays(res, radius=1.0):
