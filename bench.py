@@ -367,7 +367,7 @@ def sdfnet_probe(dev, world):
     pts = torch.rand((n, 3), device=dev) * 2 - 1
     sdf = torch.clamp(pts.norm(dim=1) - 0.5, -0.1, 0.1)
     idx = (torch.arange(n, device=dev) // 16384).to(torch.int32)
-    step = train.AutodecoderStep(net, torch.randn((512, 128), device=dev) * 0.01, world_size=1)
+    step = train.AutodecoderStep(net, torch.randn((512, 128), device=dev) * 0.01, world_size=1, points_per_shape=16384)
     ms = timed(lambda: step(pts, sdf, idx), 5)
     tf = 2.763e6 * n / (ms * 1e-3) / 1e12
     out['autodecoder_step_512x16384'] = {'mpoints_per_s': n / ms / 1e3, 'ms': ms, 'tflops': tf, 'frac_of_sustained_peak': tf / pk['bf16_tflops_sustained']}
@@ -673,7 +673,7 @@ def bench_autodecoder(args, rank, world, dev, lib):
     sdf = torch.clamp(pts.norm(dim=1) - 0.5, -0.1, 0.1)
     idx = (torch.arange(n, device=dev) // per).to(torch.int32)
     table = torch.randn((shapes, 128), generator=g).to(dev) * 0.01
-    step = train.AutodecoderStep(net, table, world_size=world)
+    step = train.AutodecoderStep(net, table, world_size=world, points_per_shape=per)
     for _ in range(max(args.warmup, 3)):
         step(pts, sdf, idx)
     torch.cuda.synchronize()

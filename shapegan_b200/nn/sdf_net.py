@@ -1,10 +1,12 @@
 """DeepSDF MLP — drop-in for model/sdf_net.py: `SDFNet(latent_code_size=128, device='cuda')`, state_dict keys
 `layers1.{0,2,4,6}.*` / `layers2.{0,2,4,6}.*`, `forward(points, latent_codes)` and the inference helpers.
 
-Extension (kept out of the reference signature's way): `forward(points, latent_codes, shape_index=None)` — when
+Extension (kept out of the reference signature's way): `forward(points, latent_codes, shape_index=None, points_per_shape=0)` — when
 `shape_index` (int [N]) is given, `latent_codes` is a [S, L] table and row i uses `latent_codes[shape_index[i]]`.
 This is what the reference's callers compute with `latent_codes[model_indices, :]` (train_sdf_autodecoder.py:80) or
-`.repeat(...)` (sdf_net.py:64, train_hybrid_progressive_gan.py:92) without materialising the [N, L] copy."""
+`.repeat(...)` (sdf_net.py:64, train_hybrid_progressive_gan.py:92) without materialising the [N, L] copy.  `points_per_shape` = P
+promises `shape_index[i] == i // P` (consecutive blocks of P points per shape, the layout of BASELINE configs[2] and of the hybrid
+GAN's grids): the backward then forms the latent gradients per shape instead of per point."""
 import os
 
 import numpy as np
@@ -100,7 +102,7 @@ class SDFNet(SavableModule):
                 ps += [seq[i].weight, seq[i].bias]
         return ps
 
-    def forward(self, points, latent_codes, shape_index=None):
+    def forward(self, points, latent_codes, shape_index=None, points_per_shape=0):
         _require_cuda(points, 'SDFNet.forward')
         n = points.shape[0]
         if n == 0:
@@ -121,7 +123,7 @@ class SDFNet(SavableModule):
                     raise RuntimeError('SDFNet.forward: shape_index out of range [0, %d)' % latent_codes.shape[0])
         elif latent_codes.shape[0] != n:
             raise RuntimeError('SDFNet.forward: %d latent rows for %d points (sizes must match, model/sdf_net.py:57)' % (latent_codes.shape[0], n))
-        out = sdfnet_apply(points.float(), latent_codes.float(), idx, self._params())
+        out = sdfnet_apply(points.float(), latent_codes.float(), idx, self._params(), seg_len=points_per_shape if idx is not None else 0)
         return out.squeeze()
 
     # ------------------------------------------------------------------ inference helpers (model/sdf_net.py:63-168)

@@ -120,7 +120,7 @@ class SDFNetFunction(Function):
     then the 16 parameters in state_dict order (layers1.{0,2,4,6}.{weight,bias}, layers2.{0,2,4,6}.{weight,bias})."""
 
     @staticmethod
-    def forward(ctx, points, latent, index, want_grad, *params):
+    def forward(ctx, points, latent, index, want_grad, seg_len, *params):
         planes = config.planes()
         n = points.shape[0]
         dev = points.device
@@ -139,12 +139,18 @@ class SDFNetFunction(Function):
             mstash = torch.empty((7, n, 8), dtype=torch.int32, device=dev) if need_graph else None      # 1-bit ReLU masks
             out = raw.sdfnet_fwd(points, latent, index, img, aux, stash, mstash)
             if need_graph:
-                x_in = raw.sdf_pack_input(points, latent, index, lat, planes, cin8)
+                # uniform segments (`seg_len` consecutive points per table row, the layout of BASELINE configs[2]): the backward needs the
+                # xyz columns only (zero-padded to one 64-column atom); the latent columns are handled per SHAPE, not per point
+                ctx.seg_len = int(seg_len) if (index is not None and seg_len and n == seg_len * latent.shape[0]) else 0
+                if ctx.seg_len:
+                    x_in = raw.f32_to_planes(points, planes, 64)
+                else:
+                    x_in = raw.sdf_pack_input(points, latent, index, lat, planes, cin8)
                 ctx.meta = (planes, n, lat, cin, cin8, index is not None, latent.shape[0])
                 ctx.w_objs = w
                 ctx.fused = True
                 ctx.mstash = mstash
-                ctx.save_for_backward(x_in, out, index if index is not None else torch.empty(0, device=dev), stash, *w)
+                ctx.save_for_backward(x_in, out, index if index is not None else torch.empty(0, device=dev), stash, latent, *w)
             return out
         ctx.fused = False
         x_in = raw.sdf_pack_input(points, latent, index, lat, planes, cin8)
@@ -185,13 +191,14 @@ class SDFNetFunction(Function):
         saved = ctx.saved_tensors
         x_in, out, index = saved[0], saved[1], saved[2]
         hstash = saved[3] if ctx.fused else None                                   # the fused forward's [7, n, 256] stash
+        latent_saved = saved[4] if ctx.fused else None
         hs = [hstash[i].unsqueeze(0) for i in range(7)] if ctx.fused else list(saved[3:10])
         w = ctx.w_objs                       # the saved parameter tensors were version-checked by autograd
         dev = gout.device
         need_points = ctx.needs_input_grad[0]
         need_latent = ctx.needs_input_grad[1]
-        need_w = [ctx.needs_input_grad[4 + 2 * i] for i in range(8)]
-        need_b = [ctx.needs_input_grad[5 + 2 * i] for i in range(8)]
+        need_w = [ctx.needs_input_grad[5 + 2 * i] for i in range(8)]
+        need_b = [ctx.needs_input_grad[6 + 2 * i] for i in range(8)]
         gw = [None] * 8
         gb = [None] * 8
         gout = gout.contiguous()
@@ -201,7 +208,7 @@ class SDFNetFunction(Function):
 
         if ctx.fused and fused_bwd_enabled():
             return _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, ctx.mstash, hs, w, gout,
-                                   need_points, need_latent, need_w, need_b)
+                                   need_points, need_latent, need_w, need_b, seg_len=getattr(ctx, 'seg_len', 0), latent=latent_saved)
 
         # ---- head: Linear(256->1) + tanh
         gh, sums = raw.rowdot_bwd(gout, out, L.ACT_TANH, hs[6], HID, w[7], True, need_w[7] or need_b[7], planes, n)
@@ -248,7 +255,7 @@ class SDFNetFunction(Function):
             if need_latent:
                 glatent = torch.zeros((lat_rows, lat), dtype=torch.float32, device=dev) if indexed else f32((n, lat))
             raw.sdf_unpack_grad(gx_a, gx_b, cin8, lat, index if indexed else None, gpoints, glatent)
-        grads = [gpoints, glatent, None, None]
+        grads = [gpoints, glatent, None, None, None]
         for i in range(8):
             grads.append(gw[i])
             grads.append(gb[i])
@@ -279,7 +286,7 @@ def _fused_pack_t(w):
 
 
 def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, index, mstash, hs, w, gout, need_points, need_latent, need_w,
-                    need_b):
+                    need_b, seg_len=0, latent=None):
     """Backward of the fused forward: ONE persistent kernel runs the whole input-gradient chain (sg_sdfnet_bwd) and leaves
     g_1..g_7 in a bf16 stash; the weight gradients, bias sums and the two input-gradient GEMMs read that stash."""
     dev = gout.device
@@ -310,13 +317,42 @@ def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, ind
         gw[i] = f32(w[i].shape)
         bg = gb[i] if bias_here else None
         if i == 0:
-            _wgrad_input(planes, g[0], x_in, cin, cin8, n, gw[0], cin, bias_grad=bg)
+            if seg_len:
+                raw.wgrad(L.MODE_DENSE, planes, g[0], HID, x_in, (1, 1, 1, 1, 64), n, gw[0], sm=cin, st=0, sc=1, m_valid=HID, c_valid=3, bias_grad=bg)
+            else:
+                _wgrad_input(planes, g[0], x_in, cin, cin8, n, gw[0], cin, bias_grad=bg)
         elif i == 4:       # W5 = [hidden 256 | xyz 3 | latent L]  (sdf_net.py:59)
             raw.wgrad(L.MODE_DENSE, planes, g[4], HID, hs[3], (1, 1, 1, 1, HID), n, gw[4], sm=HID + cin, st=0, sc=1, m_valid=HID, bias_grad=bg)
-            _wgrad_input(planes, g[4], x_in, cin, cin8, n, gw[4][:, HID:], HID + cin)
+            if seg_len:
+                raw.wgrad(L.MODE_DENSE, planes, g[4], HID, x_in, (1, 1, 1, 1, 64), n, gw[4][:, HID:], sm=HID + cin, st=0, sc=1, m_valid=HID, c_valid=3)
+            else:
+                _wgrad_input(planes, g[4], x_in, cin, cin8, n, gw[4][:, HID:], HID + cin)
         else:
             raw.wgrad(L.MODE_DENSE, planes, g[i], HID, hs[i - 1], (1, 1, 1, 1, HID), n, gw[i], sm=HID, st=0, sc=1, m_valid=HID, bias_grad=bg)
     gpoints = glatent = None
+    if seg_len and not need_points:
+        # every point of a segment shares its latent row: the latent columns of dW1 / dW5 and the latent-table gradient are products of
+        # PER-SHAPE sums of g_1 / g_5 ([S, 256], one pass over two of the seven g planes) with [S, L] / [256, L] matrices -- no K = 131
+        # GEMMs over the points, no [n, 131] input rows, no gradient scatter
+        segs = lat_rows
+        gsum = []
+        for li in (0, 4):
+            t = torch.empty((segs, HID), dtype=torch.float32, device=dev)
+            raw._call('sg_segment_colsum', raw._p(g[li]), raw._ps(g[li]), planes, segs, HID, seg_len, raw._p(t))
+            gsum.append(t)
+        z = latent.detach().float()
+        w1, w5 = w[0].detach(), w[4].detach()
+        if need_w[0]:
+            gw[0][:, 3:3 + lat] = gsum[0].t() @ z                                          # [256, S] x [S, L]: per-shape, ~1e-5 of the step's FLOPs
+        if need_w[4]:
+            gw[4][:, HID + 3:HID + 3 + lat] = gsum[1].t() @ z
+        if need_latent:
+            glatent = gsum[0] @ w1[:, 3:3 + lat] + gsum[1] @ w5[:, HID + 3:HID + 3 + lat]
+        grads = [None, glatent, None, None, None]
+        for i in range(8):
+            grads.append(gw[i])
+            grads.append(gb[i])
+        return tuple(grads)
     if need_points or need_latent:
         img = PACK_CACHE.get(w[0], 'sdf_t0', planes, lambda t, pl: _pack_lin_t(t, pl, cin, cin8))
         gx_a = torch.empty((planes, n, cin8), dtype=torch.bfloat16, device=dev)
@@ -328,7 +364,7 @@ def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, ind
         if need_latent:
             glatent = torch.zeros((lat_rows, lat), dtype=torch.float32, device=dev) if indexed else f32((n, lat))
         raw.sdf_unpack_grad(gx_a, gx_b, cin8, lat, index if indexed else None, gpoints, glatent)
-    grads = [gpoints, glatent, None, None]
+    grads = [gpoints, glatent, None, None, None]
     for i in range(8):
         grads.append(gw[i])
         grads.append(gb[i])
@@ -342,6 +378,9 @@ def _wgrad_input(planes, g, x_in, cin, cin8, n, grad_view, ld, bias_grad=None):
               bias_grad=bias_grad)
 
 
-def sdfnet_apply(points, latent, index, params):
+def sdfnet_apply(points, latent, index, params, seg_len=0):
+    """seg_len > 0: the caller guarantees that table row s owns the points [s * seg_len, (s + 1) * seg_len) (index[i] == i // seg_len)"""
     want_grad = torch.is_grad_enabled() and (points.requires_grad or latent.requires_grad or any(p.requires_grad for p in params))
-    return SDFNetFunction.apply(points, latent, index, want_grad, *params)
+    if points.requires_grad:
+        seg_len = 0          # the per-point xyz gradient takes the general path
+    return SDFNetFunction.apply(points, latent, index, want_grad, seg_len, *params)

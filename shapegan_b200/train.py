@@ -238,8 +238,9 @@ class GANStep:
 class AutodecoderStep:
     """train_sdf_autodecoder.py:77-91: the latent table is a raw leaf tensor with its own Adam."""
 
-    def __init__(self, sdf_net, latent_table, lr=1e-5, sigma=0.01, world_size=1):
-        self.net, self.sigma = sdf_net, sigma
+    def __init__(self, sdf_net, latent_table, lr=1e-5, sigma=0.01, world_size=1, points_per_shape=0):
+        """points_per_shape = P > 0: every batch is laid out shape by shape, P consecutive points each (shape_index[i] == i // P)"""
+        self.net, self.sigma, self.pps = sdf_net, sigma, points_per_shape
         self.table = latent_table.detach().clone().requires_grad_(True)
         self.nopt = FlatOptimizer(sdf_net.parameters(), 'adam', lr, world_size=world_size)
         self.lopt = FlatOptimizer([self.table], 'adam', lr, world_size=world_size)
@@ -247,12 +248,15 @@ class AutodecoderStep:
     def __call__(self, points, sdf, shape_index):
         """points [N,3], sdf [N], shape_index int32 [N] (= point_index // POINTCLOUD_SIZE, :78 with the D6 fix)."""
         self.nopt.zero_grad(); self.lopt.zero_grad()                    # :84-86
-        out = self.net(points, self.table, shape_index)                # :80,87 without materialising table[index]
+        out = self.net(points, self.table, shape_index, points_per_shape=self.pps)      # :80,87 without materialising table[index]
         # mean(z_batch^2) over the gathered rows == sum_s count_s*|table_s|^2 / (N*L): [S,L] math instead of [N,L].  The counts are
         # recomputed from the index tensor on every call (no host sync, graph-capturable): a (data_ptr, _version, numel) key is not
         # a tensor identity -- the caching allocator recycles addresses across the fresh index tensors of a data loader.
-        counts = torch.zeros(self.table.shape[0], dtype=torch.float32, device=points.device)
-        counts.index_add_(0, shape_index.long(), torch.ones((), dtype=torch.float32, device=points.device).expand(shape_index.shape[0]))
+        if self.pps:
+            counts = torch.full((self.table.shape[0],), float(self.pps), dtype=torch.float32, device=points.device)
+        else:
+            counts = torch.zeros(self.table.shape[0], dtype=torch.float32, device=points.device)
+            counts.index_add_(0, shape_index.long(), torch.ones((), dtype=torch.float32, device=points.device).expand(shape_index.shape[0]))
         reg = (counts.unsqueeze(1) * torch.pow(self.table, 2)).sum() / (points.shape[0] * self.table.shape[1])
         loss = torch.mean(torch.abs(out - sdf)) + self.sigma * reg     # :88
         with arena_backward():                                                # :89
@@ -284,7 +288,7 @@ class HybridProgressiveStep:
         if b not in self._cache:
             self._cache[b] = (self.grid.repeat((b, 1)), torch.arange(b, device=z.device, dtype=torch.int32).repeat_interleave(g))
         pts, idx = self._cache[b]
-        return self.gen(pts, z, idx).reshape(-1, self.r, self.r, self.r)              # :139-140
+        return self.gen(pts, z, idx, points_per_shape=g).reshape(-1, self.r, self.r, self.r)      # :139-140
 
     def generator_update(self, z):
         self.gopt.zero_grad(); self.dopt.zero_grad()

@@ -307,3 +307,32 @@ def test_hybrid_step_vs_reference_golden():
         assert abs(a.item() - float(c)) < 5e-3 * max(1.0, abs(float(c)))
     _after_close(g, 'dis_after.', dis, 2.2e-3)               # first RMSprop step = 10 lr = 1e-3 per weight
     _after_close(g, 'gen_after.', gen, 2.2e-3)
+
+
+def test_autodecoder_uniform_segments_equal_general_path():
+    """points_per_shape = P (per-shape latent gradients: segmented sums of g_1 / g_5 + [S, .] matrix products) against the general path
+    (K = 131 input-gradient GEMMs + scatter by index) on the same batch, bf16 fused kernels: loss, every parameter and the table."""
+    from model.sdf_net import SDFNet
+    from shapegan_b200 import config, train
+    config.set_precision('bf16')
+    shapes, per = 6, 1024
+    n = shapes * per
+    pts = rnd((n, 3), 81).cuda()
+    sdf = torch.clamp(pts.norm(dim=1) - 0.5, -0.1, 0.1)
+    idx = (torch.arange(n) // per).to(torch.int32).cuda()
+    table = (rnd((shapes, 128), 82) * 0.3).cuda()
+    res = []
+    for pps in (per, 0):
+        net = SDFNet()
+        load(net, TS.sdf_shapes(), 83)
+        step = train.AutodecoderStep(net, table, points_per_shape=pps)
+        loss = step(pts, sdf, idx)
+        grads = {k: p.grad.clone() for k, p in net.named_parameters()}
+        res.append((loss.item(), grads, step.lopt.grad.clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-6
+    for k in res[0][1]:
+        a, b = res[0][1][k], res[1][1][k]
+        err = (a - b).norm().item() / max(b.norm().item(), 1e-30)
+        assert err < 2e-2, (k, err)                   # bf16 g planes: the general path rounds g W to bf16 per point before summing
+    lat_err = (res[0][2] - res[1][2]).norm().item() / res[1][2].norm().item()
+    assert lat_err < 2e-2, lat_err
