@@ -233,7 +233,12 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
       }
     }
     tc_fence_before();
-    if (p.pair) mbar_arrive_cluster(accempty_addr[ab]); else mbar_arrive(&hdr->accempty[ab]);
+    if (p.pair) {            // one arrival per CTA: the 128 epilogue threads meet first
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (etid == 0) mbar_arrive_cluster(accempty_addr[ab]);
+    } else {
+      mbar_arrive(&hdr->accempty[ab]);
+    }
   }
 }
 
@@ -809,9 +814,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
   const int ngroups = (p.mode == SG_MODE_CONV) ? 16 : 2;
   const long long w0 = blockIdx.x >> 1, wstep = gridDim.x >> 1;
   if (tid == 0) {
-    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], 2 * kBLoaderThreads); mbar_init(&hdr->empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], 2); mbar_init(&hdr->empty[s], 1); }      // one arrival per CTA (see the loaders)
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 256);
+      mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 2);
       mbar_init(&hdr->blk_full[i], 1); mbar_init(&hdr->blk_empty[i], 1);
     }
     fence_mbar_init();
@@ -879,7 +884,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
             for (uint32_t i = (uint32_t)bt; i < pieces; i += kBLoaderThreads) cp_async16(b_dst + i * 16u, bsrc + (size_t)i * 16u, 16u);
             cp_async_commit();
             if (++pending > 1) {
-              cp_async_wait<1>(); fence_proxy_async(); mbar_arrive_cluster(full_addr[oldest]);
+              // the 96 loader threads meet on a named barrier and ONE of them arrives at the leader: 192 cluster-scope arrivals per
+              // tap on a single mbarrier (half of them remote) serialised the pair to half the single-CTA rate
+              cp_async_wait<1>(); fence_proxy_async();
+              asm volatile("bar.sync 2, 96;" ::: "memory");
+              if (bt == 0) mbar_arrive_cluster(full_addr[oldest]);
               if (++oldest == SB) oldest = 0;
               --pending;
             }
@@ -887,7 +896,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
           }
     }
     while (pending > 0) {
-      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive_cluster(full_addr[oldest]);
+      cp_async_wait<0>(); fence_proxy_async();
+      asm volatile("bar.sync 2, 96;" ::: "memory");
+      if (bt == 0) mbar_arrive_cluster(full_addr[oldest]);
       if (++oldest == SB) oldest = 0;
       --pending;
     }
@@ -1071,15 +1082,6 @@ static int igemm_tiles(const sg_igemm_args* a, bool ws_ok, TileCfg* t) {
     if (ksplit <= 0 && ws_ok && !no_split && a->out_kind != SG_OUT_F32_ATOMIC && items * 2 <= sms && kchunks >= 32 && (bn & 31) == 0) {
       int ks = (int)(sms / items);
       while (ks > 1 && kchunks / ks < 16) --ks;
-      if (ks > 1) { ksplit = ks; auto_split = true; }
-    }
-    // fp32x (hi/lo planes): the tensor core adds every K = 16 step into its fp32 accumulator with truncation (a BIASED ~2^-24 |acc| per
-    // step: 5e-5 of the output at K = 16384, profiles/r02b_parity_errors.txt) and the gradients that follow amplify a bias through
-    // their cancelling sums.  The parity mode therefore accumulates at most 8 chunks (K = 512) in TMEM and adds the chunk results in
-    // fp32 round-to-nearest (partial slabs + finish kernel): the same machinery as split-K.
-    if (ksplit <= 0 && ws_ok && !no_split && !auto_split && a->planes == 2 && a->out_kind != SG_OUT_F32_ATOMIC && kchunks > 8) {
-      int ks = std::min((kchunks + 7) / 8, 64);
-      while (ks > 1 && (size_t)ks * (size_t)t->out_rows * (size_t)a->n_pad * sizeof(float) > ((size_t)512 << 20)) ks = (ks + 1) / 2;
       if (ks > 1) { ksplit = ks; auto_split = true; }
     }
     // not enough work for the machine: narrow the N tile (keeps tensor throughput, multiplies CTAs)

@@ -137,7 +137,7 @@ def igemm(mode, planes, a, a_dims, rows, k, b_img, n_valid, out, out_ld, out_kin
     args.out_plane_stride = out.stride(0) if (out.dtype == torch.bfloat16 and out.shape[0] == 2) else 0
     args.out_kind, args.out_ld = out_kind, out_ld
     args.out_d, args.out_h, args.out_w = out_dims
-    if out_kind != L.OUT_F32_ATOMIC and (planes == 2 or rows * (8 if mode == L.MODE_CONVT else 1) * n_pad <= _SPLITK_MAX_ELEMS):
+    if out_kind != L.OUT_F32_ATOMIC and rows * (8 if mode == L.MODE_CONVT else 1) * n_pad <= _SPLITK_MAX_ELEMS:
         # few output tiles x long K (e.g. Conv3d(128->256) 8^3 -> 4^3): the library may split K over fp32 partial slabs
         nbytes = ctypes.c_size_t(0)
         L.check(L.lib().sg_igemm_plan(ctypes.byref(args), ctypes.byref(nbytes)), 'sg_igemm_plan')

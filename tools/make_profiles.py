@@ -33,6 +33,19 @@ def full(rep, dst, title):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
+    if 'prof_conv' in os.path.basename(rep) and 'dram__bytes_read.sum' in hdr:
+        # the roofline probe's DRAM traffic per launch, read by bench.py (roofline.traffic) -- tied to THIS capture
+        import json
+        r = rows[2]
+
+        def to_bytes(name):
+            v = float(r[hdr.index(name)].replace(',', ''))
+            return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(units[hdr.index(name)], 1)
+        tr = to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum')
+        with open(os.path.join(OUT, 'roofline_traffic.json'), 'w') as f:
+            json.dump({'conv_probe_dram_bytes': tr, 'kernel': r[hdr.index('Kernel Name')][:80],
+                       'source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/%s)' % os.path.basename(dst)}, f, indent=1)
+        print('wrote roofline_traffic.json', tr)
     with open(dst, 'w') as f:
         f.write('# %s\n# ncu --set full --clock-control none --import-source on  (source: %s)\n' % (title, os.path.basename(rep)))
         for r in rows[2:]:

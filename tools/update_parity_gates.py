@@ -26,10 +26,12 @@ def main():
     with open(os.path.join(REPO, 'tests', 'golden', 'parity_measured.json'), 'w') as f:
         json.dump(table, f, indent=1, sort_keys=True)
     shutil.copy(os.path.join(REPO, 'gpurun_out', 'parity_errors.txt'), os.path.join(REPO, 'profiles', '%s_parity_errors.txt' % tag))
-    over = [(r['prec'], r['case'], r['key'], r['err']) for r in rows if r['prec'] == 'fp32x' and r['note'] != 'zero' and r['err'] > 1e-3]
+    over = [(r['prec'], r['case'], r['key'], r['err']) for r in rows if r['prec'] == 'fp32x' and not r['note'].startswith('zero') and r['err'] > 1e-3]
     print('%d rows; fp32x tensors above 1e-3: %d' % (len(rows), len(over)))
-    for o in sorted(over, key=lambda t: -t[3]):
+    for o in sorted(over, key=lambda t: -t[3])[:12]:
         print('   %-6s %-28s %-44s %.2e' % o)
+    outs = [r['err'] for r in rows if r['prec'] == 'fp32x' and r['note'].split()[0] in ('out', 'scalar')]
+    print('fp32x outputs / scalars: max %.2e over %d' % (max(outs), len(outs)))
 
 
 if __name__ == '__main__':
