@@ -93,9 +93,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
-// arrive on an mbarrier that may live in another CTA of the cluster (cluster-scope release)
+// arrive on an mbarrier that may live in another CTA of the cluster.  Default (cta-scope) release semantics on purpose: what the pair
+// kernels hand over through these barriers is produced and consumed by the async proxies (cp.async / TMA writes fenced with
+// fence.proxy.async, read by each CTA's own tensor core); only the SIGNAL crosses the CTA boundary.  The cluster-scope forms
+// (.release.cluster / try_wait.acquire.cluster) compile to MEMBAR + an L1 invalidate (CCTL.IVALL) per poll and halved the kernel's
+// speed (profiles/r02c_ncu_prof_conv.txt: 36 % of all stall samples on CCTL.IVALL).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -108,10 +112,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
-// bounded wait with cluster-scope acquire (the arrivals come from the peer CTA's threads / TMA / tensor core)
+// bounded wait on a barrier whose arrivals may come from the peer CTA (threads, TMA, tensor core); cta-scope acquire, see above
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag) {
   uint64_t t0 = 0;
-  for (uint32_t spins = 1; !mbar_try_wait_cluster(bar, parity); ++spins) {
+  for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
     if ((spins & 0xfffu) == 0) {
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
