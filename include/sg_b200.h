@@ -303,7 +303,8 @@ int sg_ln_act_bwd(const void* gy, int64_t gy_ps, const void* y, int64_t y_ps, co
                   int64_t rows, int c, const float* gamma, int act, const float* stats, float* gbeta, float* ggamma, float* workspace,
                   int64_t workspace_floats, void* stream);
 int sg_rows_add_vec(const void* x, int64_t x_ps, const float* v, void* y, int64_t y_ps, int planes, int64_t rows, int c, int64_t seg_len, void* stream);
-int sg_segment_colsum(const void* x, int64_t x_ps, int planes, int segs, int c, int64_t seg_len, float* out, void* stream);
+size_t sg_segment_colsum_workspace(int segs, int c, int64_t seg_len); /* bytes; 0 = none (few long segments are split over rows) */
+int sg_segment_colsum(const void* x, int64_t x_ps, int planes, int segs, int c, int64_t seg_len, float* out, float* workspace, void* stream);
 int sg_segmax_fwd(const void* x, int64_t x_ps, int planes, int segs, int c, int64_t seg_len, void* out, int64_t out_ps, int32_t* arg, void* stream);
 int sg_segmax_move(void* big, int64_t big_ps, void* small, int64_t small_ps, int planes, int segs, int c, int64_t seg_len, const int32_t* arg,
                    int gather, void* stream);

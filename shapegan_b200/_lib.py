@@ -129,7 +129,8 @@ SYMBOLS = {
     'sg_ln_act_fwd': 'plplilippfipp',
     'sg_ln_act_bwd': 'plplplplilipipppplp',
     'sg_rows_add_vec': 'plpplililp',
-    'sg_segment_colsum': 'pliiilpp',
+    'sg_segment_colsum': 'pliiilppp',
+    'sg_segment_colsum_workspace': (c_size_t, [c_int32, c_int32, c_int64]),
     'sg_segmax_fwd': 'pliiilplpp',
     'sg_segmax_move': 'plpliiilpip',
     'sg_gp_interp': 'ppppilp',

@@ -161,15 +161,20 @@ __global__ void sg_rows_add_vec_kernel(const bf16* x, long long x_ps, const floa
   }
 }
 
-// out[s][c] = sum over the seg_len rows of segment s; grid (segments, c / 256-ish), deterministic tree inside the block
-__global__ void __launch_bounds__(256) sg_segment_colsum_kernel(const bf16* x, long long x_ps, int planes, int c, long long seg_len, float* __restrict__ out) {
+// out[s][c] = sum over the seg_len rows of segment s.  grid (segments, c / 64, row splits): few long segments (the hybrid GAN's 64^3 grids:
+// 2 segments of 262144 rows) are split over rows, every block writes its partial to part[split][s][c], sg_segment_colsum_fold adds the
+// splits in a fixed order (deterministic, no atomics).  splits == 1 writes `out` directly.
+__global__ void __launch_bounds__(256) sg_segment_colsum_kernel(const bf16* x, long long x_ps, int planes, int c, long long seg_len, float* __restrict__ out,
+                                                                int segs) {
   __shared__ float sm[8][64];
   const int seg = blockIdx.x, c0 = blockIdx.y * 64;
   const int lane8 = threadIdx.x & 7, rgrp = threadIdx.x >> 3;      // 8 pieces of 8 channels x 32 row groups
+  const long long per = (seg_len + gridDim.z - 1) / gridDim.z;
+  const long long r0 = blockIdx.z * per, r1 = min(seg_len, r0 + per);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int ch = c0 + lane8 * 8;
   if (ch < c)
-    for (long long r = rgrp; r < seg_len; r += 32) {
+    for (long long r = r0 + rgrp; r < r1; r += 32) {
       float a[8];
       ld8p(x + ((long long)seg * seg_len + r) * c + ch, x_ps, planes, a);
 #pragma unroll
@@ -188,8 +193,16 @@ __global__ void __launch_bounds__(256) sg_segment_colsum_kernel(const bf16* x, l
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += sm[w][threadIdx.x];
-    out[(long long)seg * c + c0 + threadIdx.x] = s;
+    out[((long long)blockIdx.z * segs + seg) * c + c0 + threadIdx.x] = s;
   }
+}
+
+__global__ void sg_segment_colsum_fold_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += part[(long long)k * n + i];
+  out[i] = s;
 }
 
 // ---- segment max (PointNet pooling): out[s][c] = max over the rows of segment s, arg[s][c] = the (first) row that attains it
@@ -294,12 +307,26 @@ extern "C" int sg_rows_add_vec(const void* x, int64_t x_ps, const float* v, void
   return 0;
 }
 
-extern "C" int sg_segment_colsum(const void* x, int64_t x_ps, int planes, int segs, int c, int64_t seg_len, float* out, void* stream) {
+extern "C" size_t sg_segment_colsum_workspace(int segs, int c, int64_t seg_len) {
+  const long long blocks = (long long)segs * ((c + 63) / 64);
+  long long splits = std::max<long long>(1, std::min<long long>(296 / std::max<long long>(blocks, 1), seg_len / 2048));
+  return splits > 1 ? (size_t)splits * segs * c * sizeof(float) : 0;
+}
+
+extern "C" int sg_segment_colsum(const void* x, int64_t x_ps, int planes, int segs, int c, int64_t seg_len, float* out, float* workspace, void* stream) {
   if (segs <= 0) return 0;
   if (!x || !out || (c & 7) || seg_len <= 0) return sg_fail(-1, "sg_segment_colsum: bad arguments");
-  dim3 grid(segs, (c + 63) / 64);
-  sg_segment_colsum_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)x, x_ps, planes, c, seg_len, out);
+  const size_t ws = sg_segment_colsum_workspace(segs, c, seg_len);
+  const int splits = ws ? (int)(ws / ((size_t)segs * c * sizeof(float))) : 1;
+  if (splits > 1 && !workspace) return sg_fail(-2, "sg_segment_colsum: few long segments need a workspace (sg_segment_colsum_workspace)");
+  dim3 grid(segs, (c + 63) / 64, splits);
+  sg_segment_colsum_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)x, x_ps, planes, c, seg_len, splits > 1 ? workspace : out, segs);
   SG_CUDA_CHECK_LAUNCH();
+  if (splits > 1) {
+    const long long n = (long long)segs * c;
+    sg_segment_colsum_fold_kernel<<<(int)((n + 255) / 256), 256, 0, ST(stream)>>>(workspace, splits, n, out);
+    SG_CUDA_CHECK_LAUNCH();
+  }
   return 0;
 }
 

@@ -62,9 +62,7 @@ class _RowsAddVec(Function):
         seg_len, segs = ctx.meta
         g = g.contiguous()
         p, rows, c = g.shape
-        gv = torch.empty((segs, c), dtype=torch.float32, device=g.device)
-        _call('sg_segment_colsum', _p(g), _ps(g), p, segs, c, seg_len, _p(gv))
-        return g, gv, None
+        return g, raw.segment_colsum(g, segs, seg_len), None
 
 
 def rows_add_vec(x, v, seg_len):

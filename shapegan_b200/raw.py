@@ -442,6 +442,16 @@ def sdfnet_infer(w_img, aux, n, out=None, points=None, ray_index=None, n_ptr=Non
     return out
 
 
+def segment_colsum(x, segs, seg_len):
+    """fp32 [segs, C] column sums of the consecutive seg_len-row segments of a plane tensor [P, segs * seg_len, C]"""
+    p, _, c = x.shape
+    out = torch.empty((segs, c), dtype=torch.float32, device=x.device)
+    nbytes = L.lib().sg_segment_colsum_workspace(segs, c, seg_len)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device) if nbytes else None
+    _call('sg_segment_colsum', _p(x), _ps(x), p, segs, c, seg_len, _p(out), _p(ws))
+    return out
+
+
 def grid_sphere_index(r, axis, radius):
     """int32 list (sorted) of the cells of the R^3 grid inside the sphere; `axis` fp32 [3, r] on the device"""
     idx = torch.empty(r * r * r, dtype=torch.int32, device=axis.device)

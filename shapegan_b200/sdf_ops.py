@@ -335,11 +335,7 @@ def _backward_fused(planes, n, lat, cin, cin8, indexed, lat_rows, x_in, out, ind
         # PER-SHAPE sums of g_1 / g_5 ([S, 256], one pass over two of the seven g planes) with [S, L] / [256, L] matrices -- no K = 131
         # GEMMs over the points, no [n, 131] input rows, no gradient scatter
         segs = lat_rows
-        gsum = []
-        for li in (0, 4):
-            t = torch.empty((segs, HID), dtype=torch.float32, device=dev)
-            raw._call('sg_segment_colsum', raw._p(g[li]), raw._ps(g[li]), planes, segs, HID, seg_len, raw._p(t))
-            gsum.append(t)
+        gsum = [raw.segment_colsum(g[li], segs, seg_len) for li in (0, 4)]
         z = latent.detach().float()
         w1, w5 = w[0].detach(), w[4].detach()
         if need_w[0]:

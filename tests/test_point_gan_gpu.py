@@ -78,9 +78,9 @@ def test_pointnet_pooling_kernels():
         y = point_ops._RowsAddVec.apply(xp, v, n)
         want = (xr.reshape(segs, n, ch) + v.unsqueeze(1)).reshape(-1, ch)
         assert (raw.from_planes(y) - want).abs().max().item() < 2e-2
-        gv = torch.empty((segs, ch), device='cuda')
-        point_ops._call('sg_segment_colsum', point_ops._p(xp), point_ops._ps(xp), 1, segs, ch, n, point_ops._p(gv))
-        assert rel_l2(gv, xr.reshape(segs, n, ch).sum(1)) < 1e-5
+        assert rel_l2(raw.segment_colsum(xp, segs, n), xr.reshape(segs, n, ch).sum(1)) < 1e-5
+        long = raw.to_planes(torch.randn((2 * 40000, 64), generator=gen).cuda(), 1)          # few long segments: split over rows + fold
+        assert rel_l2(raw.segment_colsum(long, 2, 40000), raw.from_planes(long).reshape(2, 40000, 64).sum(1)) < 1e-5
         # LayerNorm + ReLU
         ln = torch.nn.LayerNorm(ch).cuda()
         with torch.no_grad():
