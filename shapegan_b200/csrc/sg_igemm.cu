@@ -1244,7 +1244,7 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   if (p.halo) {
     const char* no_pair = getenv("SG_B200_NO_PAIR");
     const long long pair_tiles = p.m_tiles;
-    if (!(no_pair && no_pair[0] == '1') && (pair_tiles & 1) == 0 && (bn & 31) == 0 && bn >= 32 && p.gz % (4 * mt) == 0 && a->mask == nullptr) {
+    if (!(no_pair && no_pair[0] == '1') && (pair_tiles & 1) == 0 && (bn & 31) == 0 && bn >= 32 && p.gz % (4 * mt) == 0) {
       IgemmP q = p;
       q.pair = 1;
       q.m_tiles = p.m_tiles / 2;
