@@ -145,13 +145,30 @@ def synth_voxels(b, seed, r=32):
     return torch.clamp(torch.randn((b, r, r, r), generator=g) * 0.05, -0.1, 0.1) / 0.1      # SURVEY 8d / datasets.py:20-22
 
 
+_JSON_OUT = None      # rank 0's real stdout once file descriptor 1 has been pointed at stderr (multi-rank runs)
+
+
+def emit(line):
+    """the ONE JSON line of this run, on the process's original stdout"""
+    if _JSON_OUT is not None:
+        _JSON_OUT.write(line + '\n')
+        _JSON_OUT.flush()
+    else:
+        print(line, flush=True)
+
+
 def dist_setup(n):
+    global _JSON_OUT
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if world > 1:
-        # rank 0 prints exactly one JSON line on stdout: NCCL's INFO log (ring/tree/NVLS, nranks) goes to stderr instead of being silenced
+        # rank 0 prints exactly one JSON line on stdout, and NCCL writes its version banner / INFO log (ring, tree, NVLS, nranks) to
+        # file descriptor 1 whatever NCCL_DEBUG_FILE says: keep a private handle on the real stdout for the JSON line and point fd 1 at
+        # stderr for everything else, so the log is visible instead of silenced
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
         os.environ.setdefault('NCCL_DEBUG', 'INFO')
         os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         import torch.distributed as dist
         local = int(os.environ.get('LOCAL_RANK', '0'))
         torch.cuda.set_device(local)
@@ -657,7 +674,7 @@ def main():
             out['sdfnet'] = {'error': str(e).split('\n')[0][:200]}
     if not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(args.workload, b)
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 def bench_autodecoder(args, rank, world, dev, lib):
@@ -690,7 +707,7 @@ def bench_autodecoder(args, rank, world, dev, lib):
         return
     pk, src = peaks()
     tflops = 2.763e6 * n / (ms * 1e-3) / 1e12
-    print(json.dumps({
+    emit(json.dumps({
         'metric': 'sdfnet_autodecoder_step_points_per_s', 'value': world * n / (ms * 1e-3), 'unit': 'points/s', 'n_gpus': world, 'steps': steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': workload_name('autodecoder', shapes), 'points_per_gpu': n,
@@ -702,4 +719,12 @@ def bench_autodecoder(args, rank, world, dev, lib):
 
 
 if __name__ == '__main__':
-    main()
+    try:
+        main()
+    finally:
+        try:
+            import torch.distributed as _dist
+            if _dist.is_available() and _dist.is_initialized():
+                _dist.destroy_process_group()
+        except Exception:
+            pass
