@@ -167,8 +167,9 @@ def dist_setup(n):
         sys.stdout.flush()
         _JSON_OUT = os.fdopen(os.dup(1), 'w')
         os.dup2(2, 1)
-        os.environ.setdefault('NCCL_DEBUG', 'INFO')
-        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+        if os.environ.get('SG_B200_QUIET_NCCL') != '1':      # the GPU boxes preset NCCL_DEBUG=VERSION: ask for the init log explicitly
+            os.environ['NCCL_DEBUG'] = 'INFO'
+            os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,ENV')
         import torch.distributed as dist
         local = int(os.environ.get('LOCAL_RANK', '0'))
         torch.cuda.set_device(local)

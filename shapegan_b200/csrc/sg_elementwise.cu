@@ -142,7 +142,8 @@ __global__ void sg_bn_apply_kernel(const bf16* x, long long x_ps, bf16* y, long 
   }
 }
 
-// gx = gamma*invstd*(g - sum_g/n - xhat*sum_gxhat/n),  g = ga*act'(y)
+// gx = gamma*invstd*(g - sum_g/n - xhat*sum_gxhat/n),  g = ga*act'(y).  sums == NULL: eval mode (running statistics are constants of the
+// graph): gx = gamma*invstd*g
 __global__ void sg_bn_bwd_apply_kernel(const bf16* ga, long long ga_ps, const bf16* y, long long y_ps, const bf16* x, long long x_ps,
                                        bf16* gx, long long gx_ps, int planes, long long rows, int c, int act, const float* mean,
                                        const float* invstd, const float* gamma, const double* sums) {
@@ -161,7 +162,7 @@ __global__ void sg_bn_bwd_apply_kernel(const bf16* ga, long long ga_ps, const bf
       const int ch = p8 * 8 + j;
       const float gg = g[j] * act_grad_from_output(yy[j], act);
       const float xhat = (xx[j] - mean[ch]) * invstd[ch];
-      g[j] = gamma[ch] * invstd[ch] * (gg - (float)(sums[ch] * inv_n) - xhat * (float)(sums[c + ch] * inv_n));
+      g[j] = sums ? gamma[ch] * invstd[ch] * (gg - (float)(sums[ch] * inv_n) - xhat * (float)(sums[c + ch] * inv_n)) : gamma[ch] * invstd[ch] * gg;
     }
     store8(gx, gx_ps, planes, off, g);
   }

@@ -506,10 +506,8 @@ class _BatchNormAct(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        if not ctx.training:
-            raise NotImplementedError('shapegan_b200: backward through eval-mode BatchNorm is not implemented')
         x, y, mean, invstd, gamma = ctx.saved_tensors
-        gx, ggamma, gbeta = raw.bn_backward(gy.contiguous(), y, x, ctx.c, ctx.act, mean, invstd, gamma.detach())
+        gx, ggamma, gbeta = raw.bn_backward(gy.contiguous(), y, x, ctx.c, ctx.act, mean, invstd, gamma.detach(), training=ctx.training)
         return gx, ggamma, gbeta, None, None, None, None, None, None, None
 
 

@@ -269,15 +269,15 @@ def bn_forward(x, c, gamma, beta, act, running_mean, running_var, eps, momentum,
     return y, mean, invstd
 
 
-def bn_backward(ga, y, x, c, act, mean, invstd, gamma):
-    """returns gx (planes), ggamma, gbeta (fp32 [c])"""
+def bn_backward(ga, y, x, c, act, mean, invstd, gamma, training=True):
+    """returns gx (planes), ggamma, gbeta (fp32 [c]); training=False: mean / invstd are the running statistics (constants)"""
     planes = x.shape[0]
     rows = x[0].numel() // c
     sums = dsums(2 * c, x.device)
     _call('sg_bn_bwd_reduce', _p(ga), _ps(ga), _p(y), _ps(y), _p(x), _ps(x), planes, rows, c, act, _p(mean), _p(invstd), _p(sums))
     gx = torch.empty_like(x)
     _call('sg_bn_bwd_apply', _p(ga), _ps(ga), _p(y), _ps(y), _p(x), _ps(x), _p(gx), _ps(gx), planes, rows, c, act, _p(mean),
-          _p(invstd), _p(gamma), _p(sums))
+          _p(invstd), _p(gamma), _p(sums) if training else None)
     gbeta = torch.empty(c, dtype=torch.float32, device=x.device)
     ggamma = torch.empty(c, dtype=torch.float32, device=x.device)
     emit_sums(sums, gbeta, c)

@@ -303,3 +303,36 @@ def test_wgrad_bias_sums_ride_the_gemm(planes):
     report('wgrad-bias conv W p%d' % planes, g, wref.grad, TOL_F32)
     report('wgrad-bias conv b p%d' % planes, gb, q(dy, planes).reshape(-1, cout).sum(0), TOL_F32)
     check_error_word()
+
+
+@pytest.mark.parametrize('planes', [1, 2])
+def test_wgrad_cta_pair_multicast(planes, monkeypatch):
+    """M = 256 weight gradients on CTA pairs (the two M tiles of a pair share every gathered B tile through TMA multicast, the stage-free
+    commit goes to both CTAs) == the single-CTA kernel, dense (SDFNet layer shape, with the bias-sum MMA) and conv (128 -> 256) gathers,
+    with more than one work item per pair and a ragged row count."""
+    L, raw = _imports()
+    res = []
+    for no_pair in ('0', '1'):
+        monkeypatch.setenv('SG_B200_NO_WGRAD_PAIR', no_pair)
+        out = []
+        rows, cin, cout = 128 * 300 + 77, 256, 256
+        x, dy = rnd((rows, cin), 1), rnd((rows, cout), 2)
+        g = torch.zeros((cout, cin), dtype=torch.float32, device='cuda')
+        gb = torch.zeros((cout,), dtype=torch.float32, device='cuda')
+        raw.wgrad(L.MODE_DENSE, planes, raw.to_planes(dy, planes), cout, raw.to_planes(x, planes), (1, 1, 1, 1, cin), rows, g,
+                  sm=cin, st=0, sc=1, m_valid=cout, bias_grad=gb)
+        if no_pair == '1':
+            report('wgrad-pair ref dense p%d' % planes, g, q(dy, planes).t() @ q(x, planes), TOL_F32)
+        out += [g, gb]
+        b, r, cin, cout = 3, 8, 128, 256
+        x = rnd((b, r, r, r, cin), 3)
+        dy = rnd((b, r // 2, r // 2, r // 2, cout), 4)
+        g2 = torch.zeros((cout, cin, 4, 4, 4), dtype=torch.float32, device='cuda')
+        raw.wgrad(L.MODE_CONV, planes, raw.to_planes(dy, planes), cout, raw.to_planes(x, planes), (b, r, r, r, cin), b * (r // 2) ** 3, g2,
+                  sm=cin * 64, st=1, sc=64, m_valid=cout)
+        out.append(g2)
+        res.append(out)
+    monkeypatch.delenv('SG_B200_NO_WGRAD_PAIR')
+    for a, c in zip(res[0], res[1]):
+        assert torch.equal(a, c), 'the pair kernel must reproduce the single-CTA partial sums bit for bit (same MMAs, same order)'
+    check_error_word()
