@@ -126,6 +126,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+// cta_group::1 commit that arrives on the barrier at the same offset in every CTA of `mask` (a stage is free only when BOTH CTAs that
+// receive multicast tiles into it have finished reading it)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
 // ---- cta_group::2 flavours of the tcgen05 primitives (a CTA pair = two SMs of one TPC acting on one 256-row accumulator)
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");

@@ -61,6 +61,19 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"((uint32_t)__cvta_generic_to_shared(bar))
       : "memory");
 }
+// multicast forms: the box lands at the same shared-memory offset in every CTA of `mask` and completes bytes on each one's barrier
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar, unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(m), "r"(c0), "r"(c1), "r"((uint32_t)__cvta_generic_to_shared(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4, uint64_t* bar, unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;" ::"r"(dst),
+      "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"((uint32_t)__cvta_generic_to_shared(bar)), "h"(mask)
+      : "memory");
+}
 // CTA-pair form: the transaction bytes are reported to the mbarrier at the same offset in the pair's LEADER CTA (rank 0)
 __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(bar) & 0xFEFFFFFFu;      // clear the peer bit: CTA 0's window

@@ -33,6 +33,7 @@ struct WgradP {
   long long work_total;
   int* err;
   int use_tma, gx, gy, gz;
+  int pair;                   // CTA pairs (2-CTA cluster): the two M tiles of one (N group, row split) share every B tile through TMA multicast
   CUtensorMap tmA[2], tmB[2];
 };
 
@@ -44,20 +45,28 @@ struct WgHeader {
   uint32_t tmem_base;
 };
 
+// PAIR: launched as 2-CTA clusters.  The pair owns M tiles (2j, 2j+1) of one (N group, row split): both need the SAME gathered B tiles, so
+// each CTA issues only half of the B boxes, multicast into both CTAs' stages (the weight-gradient GEMM is bound by the bytes / TMA rows
+// it pulls per stage: 2 A atoms + 4 B atoms per CTA become 2 + 2).  A stage is recycled when BOTH CTAs' MMAs have read it: the commit
+// that frees it is multicast to both empty barriers (count 2).
+template <bool PAIR>
 __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_constant__ WgradP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   WgHeader* hdr = reinterpret_cast<WgHeader*>(smem);
   uint8_t* stage0 = smem + kWgHeader;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const long long w0 = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long wstep = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], p.use_tma ? 1 : 128); mbar_init(&hdr->empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], p.use_tma ? 1 : 128); mbar_init(&hdr->empty[s], PAIR ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128); }
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc(&hdr->tmem_base, 512);
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -85,11 +94,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
       }
       int s = 0; uint32_t ph = 0;
       const int lgx = 31 - __clz(max(p.gx, 1)), lgy = 31 - __clz(max(p.gy, 1)), lgz = 31 - __clz(max(p.gz, 1));
-      for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+      for (long long w = w0; w < p.work_total; w += wstep) {
         const uint32_t w32 = (uint32_t)w;
         const int ks = (int)(w32 % (uint32_t)p.ksplit);
         const int ng = (int)((w32 / (uint32_t)p.ksplit) % (uint32_t)p.n_groups);
-        const int mtile = (int)(w32 / ((uint32_t)p.ksplit * (uint32_t)p.n_groups));
+        const int mtile = (int)(w32 / ((uint32_t)p.ksplit * (uint32_t)p.n_groups)) * (PAIR ? 2 : 1) + (int)crank;
         const int m0 = mtile * 128;
         const int nb_atoms = min(kAtomsB, (p.n_total - ng * 256) / 64);
         const uint32_t tx_bytes = (uint32_t)((kAtomsA + nb_atoms) * p.planes) * p.tile_bytes;
@@ -119,10 +128,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
               for (int pl = 0; pl < p.planes; ++pl)
                 tma_load_2d(base + (uint32_t)(at * p.planes + pl) * p.tile_bytes, &p.tmA[pl], m0 + at * 64, (int)row0, bar);
             for (int j = 0; j < nb_atoms; ++j) {
+              if (PAIR && (uint32_t)(j & 1) != crank) continue;       // the peer issues this atom, multicast into both CTAs
               for (int pl = 0; pl < p.planes; ++pl) {
                 const uint32_t dst = bbase + (uint32_t)(j * p.planes + pl) * p.tile_bytes;
-                if (p.b_mode == SG_MODE_DENSE) tma_load_2d(dst, &p.tmB[pl], bcb[j], (int)row0, bar);
-                else tma_load_5d(dst, &p.tmB[pl], bcb[j], x0 + bkx[j], y0 + bky[j], z0 + bkz[j], n0, bar);
+                if (PAIR) {
+                  if (p.b_mode == SG_MODE_DENSE) tma_load_2d_mc(dst, &p.tmB[pl], bcb[j], (int)row0, bar, 3);
+                  else tma_load_5d_mc(dst, &p.tmB[pl], bcb[j], x0 + bkx[j], y0 + bky[j], z0 + bkz[j], n0, bar, 3);
+                } else {
+                  if (p.b_mode == SG_MODE_DENSE) tma_load_2d(dst, &p.tmB[pl], bcb[j], (int)row0, bar);
+                  else tma_load_5d(dst, &p.tmB[pl], bcb[j], x0 + bkx[j], y0 + bky[j], z0 + bkz[j], n0, bar);
+                }
               }
             }
           }
@@ -138,7 +153,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
     const int lag = max(1, S - 2);
     int pending = 0, oldest = 0;
     const int oW = p.bW >> 1, oH = p.bH >> 1, oD = p.bD >> 1;   // CONV/PATCH: rows enumerate the stride-2 output grid
-    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+    for (long long w = w0; w < p.work_total; w += wstep) {
       const int ks = (int)(w % p.ksplit);
       const int ng = (int)((w / p.ksplit) % p.n_groups);
       const int mtile = (int)(w / ((long long)p.ksplit * p.n_groups));
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
     // ================================================================ MMA ISSUER
     int s = 0; uint32_t ph = 0; int it = 0;
     const uint32_t atom_stride = (uint32_t)p.planes * p.tile_bytes;     // LBO: next 64-wide M/N atom (same plane)
-    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
+    for (long long w = w0; w < p.work_total; w += wstep, ++it) {
       const int ks = (int)(w % p.ksplit);
       const int ng = (int)((w / p.ksplit) % p.n_groups);
       const int nb_atoms = min(kAtomsB, (p.n_total - ng * 256) / 64);
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
               if (p.planes == 2) umma_bf16(tmem_base + 256, da_lo, dones, idesc_bias, 1u);
             }
           }
-          umma_commit(&hdr->empty[s]);
+          if (PAIR) umma_commit_mc(&hdr->empty[s], 3); else umma_commit(&hdr->empty[s]);
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
@@ -333,10 +348,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
     const int q = warp & 3;
     const int trow = q * 32 + lane;
     int it = 0;
-    for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
+    for (long long w = w0; w < p.work_total; w += wstep, ++it) {
       const int ks = (int)(w % p.ksplit);
       const int ng = (int)((w / p.ksplit) % p.n_groups);
-      const int mtile = (int)(w / ((long long)p.ksplit * p.n_groups));
+      const int mtile = (int)(w / ((long long)p.ksplit * p.n_groups)) * (PAIR ? 2 : 1) + (int)crank;
       const int nb_atoms = min(kAtomsB, (p.n_total - ng * 256) / 64);
       const int ab = bias_mode ? 0 : (it & 1);
       const uint32_t aph = (uint32_t)(bias_mode ? (it & 1) : ((it >> 1) & 1));
@@ -370,7 +385,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // the peer may still multicast into / commit onto this CTA's shared memory
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -503,12 +518,33 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
   const size_t smem = kWgHeader + (size_t)p.stages * p.stage_bytes + 2048;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(sg_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sg_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = (int)std::min<long long>(p.work_total, sg_num_sms());
-  sg_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
+  const int sms = sg_num_sms();
+  const char* no_pair = getenv("SG_B200_NO_WGRAD_PAIR");
+  if (p.use_tma && (p.m_tiles & 1) == 0 && !(no_pair && no_pair[0] == '1')) {
+    p.pair = 1;
+    p.work_total = (long long)(p.m_tiles / 2) * p.n_groups * p.ksplit;            // in pairs
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2u * (unsigned)std::min<long long>(p.work_total, sms / 2));
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, sg_wgrad_kernel<true>, p);
+    if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
+    sg_count_launch();
+    return 0;
+  }
+  const int grid = (int)std::min<long long>(p.work_total, sms);
+  sg_wgrad_kernel<false><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
   SG_CUDA_CHECK_LAUNCH();
   return 0;
 }

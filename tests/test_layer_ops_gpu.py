@@ -213,6 +213,29 @@ def test_rowdot_and_batchnorm_and_fade():
         close('bn%d gbeta' % c, bn.bias.grad, ref_bn.bias.grad, 5e-4)
         close('bn%d rmean' % c, bn.running_mean, ref_bn.running_mean)
         close('bn%d rvar' % c, bn.running_var, ref_bn.running_var)
+    # eval-mode BatchNorm (running statistics are constants): forward and BACKWARD (e.g. fine-tuning through a frozen generator)
+    c = 48
+    bn = torch.nn.BatchNorm3d(c).cuda()
+    bn.weight.data = rnd((c,), 21) + 1.5
+    bn.bias.data = rnd((c,), 22)
+    bn.running_mean.data = rnd((c,), 23) * 0.3
+    bn.running_var.data = rnd((c,), 24) * 0.4 + 1.0
+    bn.eval()
+    ref_bn = torch.nn.BatchNorm3d(c).cuda().double()
+    ref_bn.load_state_dict({k: v.double() if v.dtype.is_floating_point else v for k, v in bn.state_dict().items()})
+    ref_bn.eval()
+    x = rnd((3, c, 4, 4, 4), 25) * 2
+    xd = x.double().requires_grad_(True)
+    ref = F.leaky_relu(ref_bn(xd), 0.2)
+    gy = rnd(ref.shape, 26)
+    ref.backward(gy.double())
+    xp = P(ndhwc(x)).requires_grad_(True)
+    y = ops.batchnorm_act(xp, bn, ops.ACT_LRELU, c)
+    close('bn-eval fwd', ncdhw(V(y)), ref)
+    y.backward(P(ndhwc(gy)))
+    close('bn-eval gx', ncdhw(V(xp.grad)), xd.grad, 5e-4)
+    close('bn-eval ggamma', bn.weight.grad, ref_bn.weight.grad, 5e-4)
+    close('bn-eval gbeta', bn.bias.grad, ref_bn.bias.grad, 5e-4)
     # fade-in blend
     bsz, r, c, f = 2, 8, 64, 0.3
     h = rnd((bsz, r, r, r, c), 9)
