@@ -26,9 +26,10 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
-    """Compile every .cu under csrc/ to objects (parallel), link the shared library.  Returns the .so path."""
-    if not force and not _stale():
+def build_lib(force=False, verbose=False, trace=False):
+    """Compile every .cu under csrc/ to objects (parallel), link the shared library.  Returns the .so path.
+    trace: compile the clock64 stamps of tools/trace_igemm.py into the implicit-GEMM kernels (measurement builds only)."""
+    if not force and not trace and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     objdir = os.path.join(HERE, 'build')
@@ -36,7 +37,7 @@ def build_lib(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
-        cmd = [NVCC] + FLAGS + ['-c', src, '-o', obj]
+        cmd = [NVCC] + FLAGS + (['-DSG_IGEMM_TRACE'] if trace else []) + ['-c', src, '-o', obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs, log = [], []
     for src, obj, pr in procs:
@@ -59,4 +60,4 @@ def build_lib(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build_lib(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_lib(force='--force' in sys.argv, verbose='-v' in sys.argv, trace='--trace' in sys.argv))

@@ -186,6 +186,15 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
   }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------- 1-D TMA bulk copy (UBLKCP)
 // global -> shared, completion reported as transaction bytes on an mbarrier.  size % 16 == 0, 16 B aligned.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -321,11 +330,9 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
 // Conv3d(1->C,k4,s2,p1) im2col for EIGHT consecutive output-x voxels (same n, od, oh) of piece g = taps (kd = g>>1,
 // kh = 2(g&1)+{0,1}, kw = 0..3): two input lines, each fetched with 10 aligned float2 loads, feed all 8 rows x 8 taps.
 // Needs W % 16 == 0 (so 8 outputs never straddle a line and float2 pairs never straddle the border).
-__device__ __forceinline__ void patch_fill8(const float* vol_n, int D, int H, int W, int od, int oh, int ow0, int g, bool valid,
-                                            uint8_t* tile_hi, uint8_t* tile_lo, int row0) {
+__device__ __forceinline__ void patch_load8(const float* vol_n, int D, int H, int W, int od, int oh, int ow0, int g, bool valid, float (&f)[2][20]) {
   const int kd = g >> 1, kh0 = (g & 1) * 2;
   const int d = 2 * od - 1 + kd;
-  float f[2][20];
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const int h = 2 * oh - 1 + kh0 + hh;
@@ -339,6 +346,15 @@ __device__ __forceinline__ void patch_fill8(const float* vol_n, int D, int H, in
       f[hh][2 * j] = v.x; f[hh][2 * j + 1] = v.y;
     }
   }
+}
+__device__ __forceinline__ void patch_store8(const float (&f)[2][20], int g, uint8_t* tile_hi, uint8_t* tile_lo, int row0);
+__device__ __forceinline__ void patch_fill8(const float* vol_n, int D, int H, int W, int od, int oh, int ow0, int g, bool valid,
+                                            uint8_t* tile_hi, uint8_t* tile_lo, int row0) {
+  float f[2][20];
+  patch_load8(vol_n, D, H, W, od, oh, ow0, g, valid, f);
+  patch_store8(f, g, tile_hi, tile_lo, row0);
+}
+__device__ __forceinline__ void patch_store8(const float (&f)[2][20], int g, uint8_t* tile_hi, uint8_t* tile_lo, int row0) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float a0 = f[0][2 * i + 1], a1 = f[0][2 * i + 2], a2 = f[0][2 * i + 3], a3 = f[0][2 * i + 4];

@@ -26,7 +26,16 @@ constexpr int kIgemmThreads = 288;      // 4 producer warps + 1 MMA warp + 4 epi
 constexpr int kMaxStages = 6;
 constexpr int kSmemHeader = 2048;       // barriers + tmem pointer + staged bias
 constexpr int kTraceLen = 1024;
-__device__ long long g_igemm_trace[3 * kTraceLen];   // SG_B200_IGEMM_DIAG & 128: clock64 of CTA 0 {producer got slot, MMA got data, MMA issued}
+__device__ long long g_igemm_trace[3 * kTraceLen];   // SG_B200_IGEMM_DIAG & 128 in a --trace build: clock64 stamps of CTA 0 (see tr())
+
+// halo kernels, SG_B200_IGEMM_DIAG == 128: 8 channels x 128 slots of clock64 from CTA 0 (see tools/trace_igemm.py)
+constexpr int kTr = 128;
+// compiled in only with -DSG_IGEMM_TRACE (python -m shapegan_b200.build --trace): the stamps sit on the single-thread issue loops
+__device__ __forceinline__ void tr(bool on, int ch, int i) {
+#ifdef SG_IGEMM_TRACE
+  if (on && i < kTr) g_igemm_trace[ch * kTr + i] = clock64();
+#endif
+}
 
 struct IgemmP {
   int mode, planes;
@@ -50,6 +59,11 @@ struct IgemmP {
   CUtensorMap tmA2[2];   // second DENSE source
   // halo variant (sg_igemm_halo_kernel): one strided box of (8+1) x 8 x (2 mt + 1) grid points serves the 4 taps (qz, qx)
   int halo; unsigned blk_bytes; int b_stages;
+  int a_blocks;          // halo blocks in flight (2 or 3)
+  int b_tma;             // halo kernels: weight tiles by the TMA unit (1-D bulk copy; pair: 2-D box reported to the leader) instead of cp.async
+  int b_depth;           // cp.async weight tiles in flight per loader thread
+  CUtensorMap tmB;       // pair kernel, b_tma: the packed weight image as [rows][64] bf16, unswizzled (the image is pre-swizzled)
+  unsigned epi_off;      // halo kernels: byte offset of the epilogue's staging tile (128 rows x bn bf16) in shared memory, 0 = none
   int pair;              // sg_igemm_halo2_kernel: CTA pairs, tcgen05.mma.cta_group::2 (each CTA: its own 128-row tiles + half of every weight tile)
   CUtensorMap tmH;
 };
@@ -62,8 +76,8 @@ struct SmemHeader {
   uint32_t tmem_base;
   uint32_t pad_[3];
   float sbias[256];      // bias of the current N tile (epilogue broadcast reads)
-  uint64_t blk_full[2];  // halo kernel: A blocks
-  uint64_t blk_empty[2];
+  uint64_t blk_full[3];  // halo kernels: A blocks (2 or 3 of them)
+  uint64_t blk_empty[3];
 };
 
 template <class P>
@@ -72,6 +86,27 @@ __device__ __forceinline__ void decode_work(const P& p, long long w64, int& cls,
   if (p.ksplit > 1) { ks = (int)(w % (uint32_t)p.ksplit); w /= (uint32_t)p.ksplit; } else ks = 0;
   mtile = (int)(w % (uint32_t)p.m_tiles); w /= (uint32_t)p.m_tiles;
   if (p.n_tiles > 1) { nt = (int)(w % (uint32_t)p.n_tiles); cls = (int)(w / (uint32_t)p.n_tiles); } else { nt = 0; cls = (int)w; }
+}
+
+// v[0..8) *= act'(mask) for 8 packed bf16 mask values (the stored OUTPUT of the consumer's activation).  The piecewise-linear
+// activations are decided on the bf16 bit patterns (y > 0 <=> the pattern is a positive integer); the generic switch cost ~19
+// instructions per element and made every mask-fused launch 2.5-3x slower than its unmasked twin (profiles/r02e_ncu_patch.txt).
+__device__ __forceinline__ void mask_mul8(float* v, const uint4& m, int mask_act) {
+  const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+  if (mask_act == ACT_LRELU || mask_act == ACT_RELU) {
+    const float neg = (mask_act == ACT_LRELU) ? kLreluSlope : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] *= ((int)(w[i] << 16) > 0) ? 1.f : neg;
+      v[2 * i + 1] *= ((int)(w[i] & 0xffff0000u) > 0) ? 1.f : neg;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] *= act_grad_from_output(bf16lo_to_f(w[i]), mask_act);
+      v[2 * i + 1] *= act_grad_from_output(bf16hi_to_f(w[i]), mask_act);
+    }
+  }
 }
 
 template <int ACT>
@@ -89,6 +124,7 @@ struct EpiP {   // the fields the epilogue needs, copied ONCE into registers: th
   int mode, planes, n_valid, bn, mt, ksplit, m_tiles, n_tiles, bias_mod, act, mask_act, out_kind, out_ld, oD, oH, oW, aD, aH, aW, acc_bufs, acc_slot;
   long long rows, work_total, out_ps, ks_stride;
   int pair;               // CTA-pair kernel: work items are pairs of M tiles, this CTA owns tile 2*mtile + cluster rank
+  unsigned epi_off;
   const float* bias; const bf16* mask; char* out; int* err;
 };
 
@@ -98,7 +134,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
   p.mode = gp.mode; p.planes = gp.planes; p.n_valid = gp.n_valid; p.bn = gp.bn; p.mt = gp.mt; p.ksplit = gp.ksplit;
   p.m_tiles = gp.m_tiles; p.n_tiles = gp.n_tiles; p.bias_mod = gp.bias_mod; p.act = gp.act; p.mask_act = gp.mask_act;
   p.out_kind = gp.out_kind; p.out_ld = gp.out_ld; p.oD = gp.oD; p.oH = gp.oH; p.oW = gp.oW; p.aD = gp.aD; p.aH = gp.aH; p.aW = gp.aW;
-  p.pair = gp.pair; p.acc_bufs = gp.acc_bufs; p.acc_slot = gp.acc_slot; p.rows = gp.rows; p.work_total = gp.work_total; p.out_ps = gp.out_ps; p.ks_stride = gp.ks_stride;
+  p.pair = gp.pair; p.epi_off = gp.epi_off; p.acc_bufs = gp.acc_bufs; p.acc_slot = gp.acc_slot; p.rows = gp.rows; p.work_total = gp.work_total; p.out_ps = gp.out_ps; p.ks_stride = gp.ks_stride;
   p.bias = gp.bias; p.mask = gp.mask; p.out = gp.out; p.err = gp.err;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -129,9 +165,11 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
     }
     if (p.pair) mbar_wait_cluster(&hdr->accfull[ab], aph, p.err); else mbar_wait(&hdr->accfull[ab], aph, p.err);
     tc_fence_after();
+    if (etid == 0) tr((gp.diag & 128) && blockIdx.x == 0, 6, 2 * it);
     const bool tile_full = (nt * p.bn + p.bn <= p.n_valid);
     const bool fast = tile_full && (p.bn & 31) == 0 &&
                       ((p.out_kind == SG_OUT_BF16 && (p.out_ld & 7) == 0) || (p.out_kind == SG_OUT_F32 && (p.out_ld & 3) == 0 && p.mask == nullptr));
+    const bool staged = fast && p.epi_off != 0u && p.out_kind == SG_OUT_BF16 && p.planes == 1 && (p.bn == 64 || p.bn == 128);
     for (int sub = 0; sub < p.mt; ++sub) {
       const long long gr = ((long long)mtile * p.mt + sub) * kTileRows + trow;
       const bool valid = gr < p.rows;
@@ -144,7 +182,83 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
       const long long obase = orow * p.out_ld + (long long)nt * p.bn + (long long)ks * p.ks_stride;   // ks_stride: split-K partial slabs
-      if (fast) {
+      if (staged) {
+        // ---- staged stores.  A thread owns an accumulator ROW (TMEM lane), so direct stores put 16 bytes per lane at a row-pitch stride:
+        // 32 half-written sectors per instruction; the tile store took 14.7 k clocks (profiles/r02e_trace_halo.txt).  Instead each warp
+        // parks its 32 rows in shared memory (16-byte chunks XOR-swizzled by row: conflict-free both ways) and writes them out
+        // cooperatively, whole rows per instruction.  A mask tile travels the other way first, so its loads are coalesced too.
+        const uint32_t pitch = (uint32_t)p.bn * 2u;
+        const int cpr = p.bn >> 3, lgc = (cpr == 16) ? 4 : 3;           // 16-byte chunks per row (bn = 64 or 128)
+        const uint32_t stg = smem_u32(reinterpret_cast<uint8_t*>(hdr) + p.epi_off) + (uint32_t)q * 32u * pitch;
+        const uint32_t srow = stg + (uint32_t)lane * pitch;
+        const long long my_ob = valid ? obase : -1;
+        __syncwarp();
+        if (p.mask != nullptr) {
+          // all of this warp's mask loads are issued before the first use (a rolled load -> store loop serialises the round trips:
+          // 8 x ~2 k clocks per sub-tile made the masked D1 launch 3x slower than the unmasked one, profiles/r02e_trace_patch.txt)
+          uint4 mreg[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            mreg[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (k < cpr) {
+              const int i = lane + 32 * k, rr = i >> lgc, ch = i & (cpr - 1);
+              const long long ob = __shfl_sync(0xffffffffu, my_ob, rr);
+              if (ob >= 0) mreg[k] = *reinterpret_cast<const uint4*>(p.mask + ob + ch * 8);      // plain load: `mask` may alias `out`
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            if (k < cpr) {
+              const int i = lane + 32 * k, rr = i >> lgc, ch = i & (cpr - 1);
+              st_shared_v4(stg + (uint32_t)rr * pitch + (uint32_t)((ch ^ (rr & 7)) << 4), mreg[k]);
+            }
+          }
+          __syncwarp();
+        }
+        for (int c0 = 0; c0 < p.bn; c0 += 64) {        // bn = 64 or 128: two 32-column TMEM loads in flight per wait
+          uint32_t r[2][32];
+          __syncwarp();
+          tmem_ld32(t_addr + c0, r[0]);
+          tmem_ld32(t_addr + c0 + 32, r[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cb = c0 + 32 * h;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = add_bias ? *reinterpret_cast<const float4*>(sbias + cb + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[j] = act_t<ACT>(__uint_as_float(r[h][j]) + b.x, p.act);
+              v[j + 1] = act_t<ACT>(__uint_as_float(r[h][j + 1]) + b.y, p.act);
+              v[j + 2] = act_t<ACT>(__uint_as_float(r[h][j + 2]) + b.z, p.act);
+              v[j + 3] = act_t<ACT>(__uint_as_float(r[h][j + 3]) + b.w, p.act);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint32_t slot = srow + (uint32_t)((((cb + j) >> 3) ^ (lane & 7)) << 4);
+              if (p.mask != nullptr) {
+                const uint4 m = ld_shared_v4(slot);
+                mask_mul8(v + j, m, p.mask_act);
+              }
+              uint4 hi;
+              hi.x = pack_bf16x2(v[j], v[j + 1]); hi.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              hi.z = pack_bf16x2(v[j + 4], v[j + 5]); hi.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              st_shared_v4(slot, hi);
+            }
+          }
+        }
+        __syncwarp();
+        if (!(gp.diag & 8)) {
+          bf16* const outp = reinterpret_cast<bf16*>(p.out);
+          for (int i = lane; i < 32 * cpr; i += 32) {
+            const int rr = i >> lgc, ch = i & (cpr - 1);
+            const long long ob = __shfl_sync(0xffffffffu, my_ob, rr);
+            const uint4 val = ld_shared_v4(stg + (uint32_t)rr * pitch + (uint32_t)((ch ^ (rr & 7)) << 4));
+            if (ob >= 0) *reinterpret_cast<uint4*>(outp + ob + ch * 8) = val;
+          }
+        }
+        __syncwarp();
+      } else if (fast) {
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
           uint32_t r[32];
           __syncwarp();
@@ -167,10 +281,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 const uint4 m = *reinterpret_cast<const uint4*>(mk + j);     // plain load: `mask` may alias `out` (in-place activation backward)
-                v[j] *= act_grad_from_output(bf16lo_to_f(m.x), p.mask_act); v[j + 1] *= act_grad_from_output(bf16hi_to_f(m.x), p.mask_act);
-                v[j + 2] *= act_grad_from_output(bf16lo_to_f(m.y), p.mask_act); v[j + 3] *= act_grad_from_output(bf16hi_to_f(m.y), p.mask_act);
-                v[j + 4] *= act_grad_from_output(bf16lo_to_f(m.z), p.mask_act); v[j + 5] *= act_grad_from_output(bf16hi_to_f(m.z), p.mask_act);
-                v[j + 6] *= act_grad_from_output(bf16lo_to_f(m.w), p.mask_act); v[j + 7] *= act_grad_from_output(bf16hi_to_f(m.w), p.mask_act);
+                mask_mul8(v + j, m, p.mask_act);
               }
             }
 #pragma unroll
@@ -232,6 +343,7 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
         }
       }
     }
+    if (etid == 0) tr((gp.diag & 128) && blockIdx.x == 0, 6, 2 * it + 1);
     tc_fence_before();
     if (p.pair) {            // one arrival per CTA: the 128 epilogue threads meet first
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -252,7 +364,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], (p.use_tma ? kBLoaderThreads : kProducerThreads) + 1); mbar_init(&hdr->empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&hdr->full[s], (p.use_tma ? (p.b_tma ? 0 : kBLoaderThreads) : kProducerThreads) + 1); mbar_init(&hdr->empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128); }
     fence_mbar_init();
   }
@@ -291,7 +403,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     if (warp == 0 && elect_one()) {
       tma_prefetch_desc(&p.tmA[0]);
       if (p.planes == 2) tma_prefetch_desc(&p.tmA[1]);
-      int s = 0; uint32_t ph = 0;
+      int s = 0; uint32_t ph = 0; int tcnt = 0;
       const int c1chunks = (p.aC + 63) >> 6;
       // power-of-two row grid: tile origin by shifts/masks, once per tile (no 64-bit division in the K loop)
       const int lgx = 31 - __clz(max(p.gx, 1)), lgy = 31 - __clz(max(p.gy, 1)), lgz = 31 - __clz(max(p.gz, 1));
@@ -314,7 +426,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
         if (p.mode != SG_MODE_DENSE) { tap = (k0 * 64) / p.aC; c0 = k0 * 64 - tap * p.aC; }
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
-          if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[kc - k0] = clock64();
+          tr((p.diag & 128) && blockIdx.x == 0, 0, tcnt++);
           uint64_t* bar = &hdr->full[s];
           const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
           int ox = 0, oy = 0, oz = 0;
@@ -324,7 +436,13 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             oz = pd ? 1 - td : -td; oy = phh ? 1 - th : -th; ox = pw ? 1 - tw : -tw;
           }
           {
-            mbar_arrive_expect_tx(bar, (p.diag & 1) ? 0u : p.a_stage_bytes);
+            const uint32_t b_bytes = (p.b_tma && !(p.diag & 2)) ? (uint32_t)(p.planes * p.bn) * 128u : 0u;
+            mbar_arrive_expect_tx(bar, ((p.diag & 1) ? 0u : p.a_stage_bytes) + b_bytes);
+            if (b_bytes) {        // the packed weight tile of this K chunk: one linear bulk copy per plane
+              const char* bsrc = p.b + ((((size_t)cls * p.kchunks + kc) * p.planes) * p.n_pad + (size_t)nt * p.bn) * 128;
+              for (int pl = 0; pl < p.planes; ++pl)
+                bulk_g2s(a_base + p.a_stage_bytes + (uint32_t)(pl * p.bn) * 128u, bsrc + (size_t)pl * p.n_pad * 128, (uint32_t)p.bn * 128u, bar);
+            }
             for (int sub = 0; sub < ((p.diag & 1) ? 0 : p.mt); ++sub) {
               for (int pl = 0; pl < p.planes; ++pl) {
                 const uint32_t dst = a_base + (uint32_t)(sub * p.planes + pl) * kTileBytes;
@@ -348,10 +466,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     // per-SM load limit, ~3.5 clk per gathered 128-byte row -- to the A tiles alone (loads-only 48 -> 44 us on Conv3d 64->128).
     // Gathering A rows this way as well was measured 3x slower than TMA.  Completion: wait_group (one stage behind),
     // generic->async proxy fence, arrive.
-    if (warp >= 1) {
+    if (warp >= 1 && !p.b_tma) {
       const int bt = tid - 32;                                   // 0..95
       int s = 0; uint32_t ph = 0;
       int pending = 0, oldest = 0;
+      const int depth = min(S - 1, p.b_depth);                               // weight tiles in flight per loader thread (see the halo kernels)
       const uint32_t pieces = (uint32_t)p.planes * (uint32_t)p.bn * 8u;      // 16-byte pieces per stage
       const size_t bplane = (size_t)p.n_pad * 128;
       for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
@@ -374,8 +493,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             }
           }
           cp_async_commit();
-          if (++pending > 1) {
-            cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+          if (++pending > depth) {
+            cp_async_wait_dyn(depth); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
             if (++oldest == S) oldest = 0;
             --pending;
           }
@@ -384,7 +503,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
         }
       }
       while (pending > 0) {
-        cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+        cp_async_wait_dyn(pending - 1); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
         if (++oldest == S) oldest = 0;
         --pending;
       }
@@ -395,9 +514,53 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     int s = 0; uint32_t ph = 0;
     // loads run `lag` stages ahead of the completion signal: keeps (lag+1) x stage bytes in flight per SM
     const int lag = max(1, S - 2);
-    int pending = 0, oldest = 0;
+    int pending = 0, oldest = 0, tslot = 0, tsig = 0;
     const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
-    const bool patch_fast = p.mode == SG_MODE_PATCH && (p.aW & 15) == 0;   // rows decoded inside patch_fill8's caller
+    const bool patch_fast = p.mode == SG_MODE_PATCH && (p.aW & 15) == 0;
+    if (patch_fast) {
+      // ---- Conv3d(1 -> N) on the fp32 volume, W % 16 == 0 (every BASELINE resolution): K = 64 taps = ONE chunk per work item.
+      // Thread (rb = tid >> 3, g = tid & 7) fills 8 consecutive output-x rows of 16-byte piece g (taps kd = g >> 1, kh = 2 (g & 1) + {0, 1},
+      // kw = 0..3) from two register-blocked input lines.  The loads of BOTH sub-tiles are issued before any conversion (one exposed
+      // memory round trip per stage), and the stage is signalled at once: it was written with ordinary stores, nothing is in flight.
+      const float* vol = reinterpret_cast<const float*>(p.a_ptr);
+      const int oW = p.aW >> 1, oH = p.aH >> 1, oD = p.aD >> 1;
+      for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+        int cls, nt, mtile, ks;
+        decode_work(p, w, cls, nt, mtile, ks);
+        float f[2][2][20];
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          if (sub >= p.mt) break;
+          const long long gr0 = ((long long)mtile * p.mt + sub) * kTileRows + rb * 8;
+          const bool v = gr0 < p.rows;
+          const uint32_t r32 = (uint32_t)(v ? gr0 : 0);
+          const int ow0 = (int)(r32 % (uint32_t)oW); uint32_t t2 = r32 / (uint32_t)oW;
+          const int oh = (int)(t2 % (uint32_t)oH); t2 /= (uint32_t)oH;
+          const int od = (int)(t2 % (uint32_t)oD); const uint32_t n = t2 / (uint32_t)oD;
+          patch_load8(vol + (size_t)n * p.aD * p.aH * p.aW, p.aD, p.aH, p.aW, od, oh, ow0, g, v, f[sub]);
+        }
+        mbar_wait(&hdr->empty[s], ph ^ 1, p.err);            // (the loads above are already in flight)
+        if (tid == 0) tr((p.diag & 128) && blockIdx.x == 0, 1, tslot++);
+        uint8_t* st = stage0 + (size_t)s * p.stage_bytes;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          if (sub >= p.mt) break;
+          uint8_t* tile = st + (size_t)(sub * p.planes) * kTileBytes;
+          patch_store8(f[sub], g, tile, p.planes == 2 ? tile + kTileBytes : nullptr, rb * 8);
+        }
+        if (warp == 0 && elect_one()) {
+          mbar_arrive_expect_tx(&hdr->full[s], b_tile_bytes * p.planes);
+          const uint32_t b_dst = smem_u32(st) + p.a_stage_bytes;
+          for (int pl = 0; pl < p.planes; ++pl) {
+            const char* src = p.b + ((((size_t)cls * p.kchunks) * p.planes + pl) * p.n_pad + (size_t)nt * p.bn) * 128;
+            bulk_g2s(b_dst + pl * b_tile_bytes, src, b_tile_bytes, &hdr->full[s]);
+          }
+        }
+        fence_proxy_async(); mbar_arrive(&hdr->full[s]);
+        if (tid == 0) tr((p.diag & 128) && blockIdx.x == 0, 2, tsig++);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    } else
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
       int cls, nt, mtile, ks;
       decode_work(p, w, cls, nt, mtile, ks);
@@ -409,7 +572,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           ri_n[sub][i] = -1; ri_c[sub][i] = 0;
-          if (sub < p.mt && !patch_fast) {
+          if (sub < p.mt) {
             long long gr = ((long long)mtile * p.mt + sub) * kTileRows + rb + 16 * i;
             if (gr < p.rows) {
               if (p.mode == SG_MODE_DENSE) {
@@ -437,24 +600,10 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
       const int k0 = ks * cps, k1 = min(p.kchunks, k0 + cps);
       for (int kc = k0; kc < k1; ++kc) {
         mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+        if (tid == 0) tr((p.diag & 128) && blockIdx.x == 0, 1, tslot++);
         uint8_t* st = stage0 + (size_t)s * p.stage_bytes;
         const uint32_t a_base = smem_u32(st);
-        if (patch_fast) {
-          // fast im2col: thread (rg = tid>>3, g) fills 8 consecutive output-x rows of piece g from two register-blocked lines
-          const float* vol = reinterpret_cast<const float*>(p.a_ptr);
-          const int oW = p.aW >> 1, oH = p.aH >> 1, oD = p.aD >> 1;
-          for (int sub = 0; sub < p.mt; ++sub) {
-            const long long gr0 = ((long long)mtile * p.mt + sub) * kTileRows + rb * 8;
-            const bool v = gr0 < p.rows;
-            const uint32_t r32 = (uint32_t)(v ? gr0 : 0);
-            const int ow0 = (int)(r32 % (uint32_t)oW); uint32_t t2 = r32 / (uint32_t)oW;
-            const int oh = (int)(t2 % (uint32_t)oH); t2 /= (uint32_t)oH;
-            const int od = (int)(t2 % (uint32_t)oD); const uint32_t n = t2 / (uint32_t)oD;
-            uint8_t* tile = st + (size_t)(sub * p.planes) * kTileBytes;
-            patch_fill8(vol + (size_t)n * p.aD * p.aH * p.aW, p.aD, p.aH, p.aW, od, oh, ow0, g, v, tile,
-                        p.planes == 2 ? tile + kTileBytes : nullptr, rb * 8);
-          }
-        } else if (p.mode == SG_MODE_PATCH) {
+        if (p.mode == SG_MODE_PATCH) {
           // single-channel fp32 volume: K = 64 taps, piece g = taps [8g, 8g+8) = (kd = g>>1, kh = 2(g&1)+{0,1}, kw = 0..3)
           const float* vol = reinterpret_cast<const float*>(p.a_ptr);
           const int kd = g >> 1, khb = (g & 1) * 2;
@@ -547,11 +696,19 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             bulk_g2s(b_dst + pl * b_tile_bytes, src, b_tile_bytes, &hdr->full[s]);
           }
         }
-        cp_async_commit();
-        if (++pending > lag) {
-          cp_async_wait_dyn(lag); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
-          if (++oldest == S) oldest = 0;
-          --pending;
+        if (p.mode == SG_MODE_PATCH) {
+          // the im2col tile was written with ordinary stores: the stage is complete now (running `lag` stages behind, as the cp.async
+          // gathers must, kept the first MMA waiting for FOUR tiles -- 27 k of the layer's 77 k clocks, profiles/r02e_trace_patch.txt)
+          fence_proxy_async(); mbar_arrive(&hdr->full[s]);
+          if (tid == 0) tr((p.diag & 128) && blockIdx.x == 0, 2, tsig++);
+        } else {
+          cp_async_commit();
+          if (++pending > lag) {
+            cp_async_wait_dyn(lag); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+            if (tid == 0) tr((p.diag & 128) && blockIdx.x == 0, 2, tsig++);
+            if (++oldest == S) oldest = 0;
+            --pending;
+          }
         }
         if (++s == S) { s = 0; ph ^= 1; }
       }
@@ -565,7 +722,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
     // ================================================================ MMA ISSUER
     // ONE elected thread runs the whole loop (barrier polls included)
     const uint32_t idesc = umma_idesc(128, p.bn, false, false);
-    int s = 0; uint32_t ph = 0; int it = 0;
+    int s = 0; uint32_t ph = 0; int it = 0; int tcnt = 0;
     if (elect_one())
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
       int cls, nt, mtile, ks;
@@ -578,7 +735,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
       for (int kc = k0; kc < k1; ++kc) {
         mbar_wait(&hdr->full[s], ph, p.err);
         tc_fence_after();
-        if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[kTraceLen + kc - k0] = clock64();
+        tr((p.diag & 128) && blockIdx.x == 0, 4, tcnt);
         {
           const uint32_t a_base = smem_u32(stage0 + (size_t)s * p.stage_bytes);
           const uint32_t b_base = a_base + p.a_stage_bytes;
@@ -600,7 +757,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_kernel(const __grid
             }
           }
           umma_commit(&hdr->empty[s]);
-          if ((p.diag & 128) && blockIdx.x == 0 && kc - k0 < kTraceLen) g_igemm_trace[2 * kTraceLen + kc - k0] = clock64();
+          tr((p.diag & 128) && blockIdx.x == 0, 5, tcnt++);
         }
         if (++s == S) { s = 0; ph ^= 1; }
       }
@@ -646,22 +803,45 @@ __device__ __forceinline__ int halo_tap(const IgemmP& p, int grp, int t4) {
   return (1 - qz) * 4 + th * 2 + (1 - qx);
 }
 
+// One filter tap of the halo kernels: mt sub-tiles x 4 K steps (K = 16 each) of one 64-channel chunk.  The single issuing thread is the
+// pace-setter of the narrow-N layers (ConvT 128->64: 8 MMAs of 32 clk per tap), so the descriptors are not rebuilt per MMA: their
+// constant fields live in `a_hi` / `b_hi`, the start-address field (14 bits of address >> 4) is advanced by plain adds.
+template <bool PAIR>
+__device__ __forceinline__ void halo_issue_tap(uint32_t d0, uint32_t acc_slot, int mt, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                               uint32_t idesc, bool first) {
+  constexpr uint32_t kSubStep = (2u * 8u * 9u * 128u) >> 4;        // two z planes of the halo block per sub-tile
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub) {
+    if (sub < mt) {
+      const uint32_t d_addr = d0 + (uint32_t)sub * acc_slot;
+      const uint32_t al = a_lo + (uint32_t)sub * kSubStep;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(al + 2u * kk);
+        const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * kk);
+        if (PAIR) umma2_bf16(d_addr, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+        else umma_bf16(d_addr, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const __grid_constant__ IgemmP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   uint8_t* blk0 = smem + kSmemHeader;
-  uint8_t* bst0 = blk0 + 2 * (size_t)p.blk_bytes;
+  uint8_t* bst0 = blk0 + (size_t)p.a_blocks * p.blk_bytes;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool tron = (p.diag & 128) && blockIdx.x == 0;
+  if (tid == 0) tr(tron, 7, 0);
   const int SB = p.b_stages;
   const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
   const int cchunks = p.aC >> 6;
   const int ngroups = (p.mode == SG_MODE_CONV) ? 16 : 2;
   if (tid == 0) {
-    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], kBLoaderThreads); mbar_init(&hdr->empty[s], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128);
-      mbar_init(&hdr->blk_full[i], 1); mbar_init(&hdr->blk_empty[i], 1);
-    }
+    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], p.b_tma ? 1 : kBLoaderThreads); mbar_init(&hdr->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 128); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&hdr->blk_full[i], 1); mbar_init(&hdr->blk_empty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc(&hdr->tmem_base, 512);
@@ -669,6 +849,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  if (tid == 0) tr(tron, 7, 1);
   if ((smem_u32(smem) & 1023u) != 0) {
     if (tid == 0) atomicExch(p.err, kErrSmemAlign);
     __trap();
@@ -678,7 +859,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const _
     // ================================================================ TMA producer: one halo block per (group, channel chunk)
     if (elect_one()) {
       tma_prefetch_desc(&p.tmH);
-      int bi = 0; uint32_t bph = 0;
+      int bi = 0; uint32_t bph = 0; int tb = 0;
       const int lgz = 31 - __clz(max(p.gz, 1));
       for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
         int cls, nt, mtile, ks;
@@ -697,18 +878,43 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const _
           }
           for (int cc = 0; cc < cchunks; ++cc) {
             mbar_wait(&hdr->blk_empty[bi], bph ^ 1, p.err);
+            tr(tron, 0, tb++);
             mbar_arrive_expect_tx(&hdr->blk_full[bi], p.blk_bytes);
             tma_load_5d(smem_u32(blk0 + (size_t)bi * p.blk_bytes), &p.tmH, cc * 64, x, y, z, n0, &hdr->blk_full[bi]);
-            if (++bi == 2) { bi = 0; bph ^= 1; }
+            if (++bi == p.a_blocks) { bi = 0; bph ^= 1; }
           }
         }
+      }
+    }
+  } else if (warp < 4 && p.b_tma) {
+    // ================================================================ weight tiles by 1-D bulk copies (one elected thread of warp 1)
+    if (warp == 1 && elect_one()) {
+      int s = 0; uint32_t ph = 0; int tl = 0;
+      for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
+        int cls, nt, mtile, ks;
+        decode_work(p, w, cls, nt, mtile, ks);
+        const char* bcls = p.b + ((size_t)cls * p.kchunks * p.n_pad + (size_t)nt * p.bn) * 128;
+        for (int grp = 0; grp < ngroups; ++grp)
+          for (int cc = 0; cc < cchunks; ++cc)
+            for (int t4 = 0; t4 < 4; ++t4) {
+              const int kc = halo_tap(p, grp, t4) * cchunks + cc;
+              mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+              tr(tron, 1, tl++);
+              mbar_arrive_expect_tx(&hdr->full[s], b_tile_bytes);
+              bulk_g2s(smem_u32(bst0 + (size_t)s * b_tile_bytes), bcls + (size_t)kc * p.n_pad * 128, b_tile_bytes, &hdr->full[s]);
+              if (++s == SB) { s = 0; ph ^= 1; }
+            }
       }
     }
   } else if (warp < 4) {
     // ================================================================ weight-tile loaders (warps 1-3, cp.async), K sequence order
     const int bt = tid - 32;
     int s = 0; uint32_t ph = 0;
-    int pending = 0, oldest = 0;
+    int pending = 0, oldest = 0, tl = 0, ta = 0;
+    // committed weight tiles a loader thread runs ahead of its completion signal.  One: the 16-byte LDGSTS path moves ~23 B/clk per SM however
+    // many are queued; with two ahead ConvT 128->64 went from 55 to 70 us, with five the landing time of a tile went from ~1400 to ~9000 clk
+    // (profiles/r02e_trace_halo.txt, r02e_sweep_cfgs.txt) -- deeper is slower, not faster.
+    const int depth = min(SB - 1, p.b_depth);
     const uint32_t pieces = (uint32_t)p.bn * 8u;
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x) {
       int cls, nt, mtile, ks;
@@ -720,11 +926,13 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const _
             const int kc = halo_tap(p, grp, t4) * cchunks + cc;
             const char* bsrc = bcls + (size_t)kc * p.n_pad * 128;
             mbar_wait(&hdr->empty[s], ph ^ 1, p.err);
+            if (bt == 0) tr(tron, 1, tl++);
             const uint32_t b_dst = smem_u32(bst0 + (size_t)s * b_tile_bytes);
             for (uint32_t i = (uint32_t)bt; i < pieces; i += kBLoaderThreads) cp_async16(b_dst + i * 16u, bsrc + (size_t)i * 16u, 16u);
             cp_async_commit();
-            if (++pending > 1) {
-              cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+            if (++pending > depth) {
+              cp_async_wait_dyn(depth); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+              if (bt == 0) tr(tron, 2, ta++);
               if (++oldest == SB) oldest = 0;
               --pending;
             }
@@ -732,47 +940,46 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const _
           }
     }
     while (pending > 0) {
-      cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
+      cp_async_wait_dyn(pending - 1); fence_proxy_async(); mbar_arrive(&hdr->full[oldest]);
       if (++oldest == SB) oldest = 0;
       --pending;
     }
   } else if (warp == 4) {
     // ================================================================ MMA issuer (one elected thread)
     const uint32_t idesc = umma_idesc(128, p.bn, false, false);
+    const uint32_t a_hi = (uint32_t)(umma_desc(0, 16, 9 * 128) >> 32), b_hi = (uint32_t)(umma_desc(0, 16, 1024) >> 32);
+    const uint32_t a_lbo = (16u >> 4) << 16;      // LBO field (bits 16..29) rides in the low word
+    const int mt_ = p.mt; const uint32_t acc_slot_ = (uint32_t)p.acc_slot;
     int s = 0; uint32_t ph = 0; int it = 0;
-    int bi = 0; uint32_t bph = 0;
+    int bi = 0; uint32_t bph = 0; int tb = 0, tt = 0;
     if (elect_one())
     for (long long w = blockIdx.x; w < p.work_total; w += gridDim.x, ++it) {
       const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
       const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
       mbar_wait(&hdr->accempty[ab], aph ^ 1, p.err);
+      tr(tron, 7, 2);
       tc_fence_after();
       bool first = true;
       for (int grp = 0; grp < ngroups; ++grp)
         for (int cc = 0; cc < cchunks; ++cc) {
           mbar_wait(&hdr->blk_full[bi], bph, p.err);
+          tr(tron, 3, tb++);
           const uint32_t blk = smem_u32(blk0 + (size_t)bi * p.blk_bytes);
           for (int t4 = 0; t4 < 4; ++t4) {
             const int qz = t4 >> 1, qx = t4 & 1;
             mbar_wait(&hdr->full[s], ph, p.err);
+            tr(tron, 4, tt);
             tc_fence_after();
             const uint32_t b_base = smem_u32(bst0 + (size_t)s * b_tile_bytes);
-            for (int sub = 0; sub < p.mt; ++sub) {
-              const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
-              const uint32_t a_view = blk + (uint32_t)(((sub * 2 + qz) * 8) * 9 + qx) * 128u;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t da = umma_desc(a_view + kk * 32, 16, 9 * 128);
-                const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
-                umma_bf16(d_addr, da, db, idesc, (first && kk == 0) ? 0u : 1u);
-              }
-            }
+            halo_issue_tap<false>(tmem_base + (uint32_t)(ab * mt_ * acc_slot_), acc_slot_, mt_,
+                                  (((blk & 0x3FFFFu) >> 4) + (uint32_t)((qz * 72 + qx) * 8)) | a_lbo, ((b_base & 0x3FFFFu) >> 4) | a_lbo, a_hi, b_hi, idesc, first);
             first = false;
             umma_commit(&hdr->empty[s]);
+            tr(tron, 5, tt++);
             if (++s == SB) { s = 0; ph ^= 1; }
           }
           umma_commit(&hdr->blk_empty[bi]);
-          if (++bi == 2) { bi = 0; bph ^= 1; }
+          if (++bi == p.a_blocks) { bi = 0; bph ^= 1; }
         }
       umma_commit(&hdr->accfull[ab]);
     }
@@ -787,6 +994,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) sg_igemm_halo_kernel(const _
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) tr(tron, 7, 3);
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -804,8 +1012,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
   extern __shared__ __align__(1024) uint8_t smem[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   uint8_t* blk0 = smem + kSmemHeader;
-  uint8_t* bst0 = blk0 + 2 * (size_t)p.blk_bytes;
+  uint8_t* bst0 = blk0 + (size_t)p.a_blocks * p.blk_bytes;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool tron = (p.diag & 128) && blockIdx.x == 0;
+  if (tid == 0) tr(tron, 7, 0);
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
   const int SB = p.b_stages;
@@ -814,11 +1024,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
   const int ngroups = (p.mode == SG_MODE_CONV) ? 16 : 2;
   const long long w0 = blockIdx.x >> 1, wstep = gridDim.x >> 1;
   if (tid == 0) {
-    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], 2); mbar_init(&hdr->empty[s], 1); }      // one arrival per CTA (see the loaders)
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 2);
-      mbar_init(&hdr->blk_full[i], 1); mbar_init(&hdr->blk_empty[i], 1);
-    }
+    for (int s = 0; s < SB; ++s) { mbar_init(&hdr->full[s], p.b_tma ? 1 : 2); mbar_init(&hdr->empty[s], 1); }      // cp.async: one arrival per CTA (see the loaders)
+    for (int i = 0; i < 2; ++i) { mbar_init(&hdr->accfull[i], 1); mbar_init(&hdr->accempty[i], 2); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&hdr->blk_full[i], 1); mbar_init(&hdr->blk_empty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc2(&hdr->tmem_base, 512);
@@ -826,6 +1034,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  if (tid == 0) tr(tron, 7, 1);
   if ((smem_u32(smem) & 1023u) != 0) {
     if (tid == 0) atomicExch(p.err, kErrSmemAlign);
     __trap();
@@ -835,7 +1044,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
     // ================================================================ TMA producer: this CTA's halo blocks; bytes reported to the leader
     if (elect_one()) {
       tma_prefetch_desc(&p.tmH);
-      int bi = 0; uint32_t bph = 0;
+      int bi = 0; uint32_t bph = 0; int tb = 0;
       const int lgz = 31 - __clz(max(p.gz, 1));
       for (long long w = w0; w < p.work_total; w += wstep) {
         int cls, nt, mtile, ks;
@@ -855,18 +1064,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
           }
           for (int cc = 0; cc < cchunks; ++cc) {
             mbar_wait_cluster(&hdr->blk_empty[bi], bph ^ 1, p.err);
+            tr(tron, 0, tb++);
             if (leader) mbar_arrive_expect_tx(&hdr->blk_full[bi], 2u * p.blk_bytes);
             tma_load_5d_2sm(smem_u32(blk0 + (size_t)bi * p.blk_bytes), &p.tmH, cc * 64, x, y, z, n0, &hdr->blk_full[bi]);
-            if (++bi == 2) { bi = 0; bph ^= 1; }
+            if (++bi == p.a_blocks) { bi = 0; bph ^= 1; }
           }
         }
+      }
+    }
+  } else if (warp < 4 && p.b_tma) {
+    // ================================================================ weight tiles by TMA: this CTA's half of every tap's tile, bytes reported to the leader
+    if (warp == 1 && elect_one()) {
+      tma_prefetch_desc(&p.tmB);
+      int s = 0; uint32_t ph = 0; int tl = 0;
+      for (long long w = w0; w < p.work_total; w += wstep) {
+        int cls, nt, mtile, ks;
+        decode_work(p, w, cls, nt, mtile, ks);
+        const int row0 = cls * p.kchunks * p.n_pad + nt * p.bn + (int)crank * (p.bn / 2);
+        for (int grp = 0; grp < ngroups; ++grp)
+          for (int cc = 0; cc < cchunks; ++cc)
+            for (int t4 = 0; t4 < 4; ++t4) {
+              const int kc = halo_tap(p, grp, t4) * cchunks + cc;
+              mbar_wait_cluster(&hdr->empty[s], ph ^ 1, p.err);
+              tr(tron, 1, tl++);
+              if (leader) mbar_arrive_expect_tx(&hdr->full[s], 2u * b_half_bytes);
+              tma_load_2d_2sm(smem_u32(bst0 + (size_t)s * b_half_bytes), &p.tmB, 0, row0 + kc * p.n_pad, &hdr->full[s]);
+              if (++s == SB) { s = 0; ph ^= 1; }
+            }
       }
     }
   } else if (warp < 4) {
     // ================================================================ weight-tile loaders: this CTA's HALF (rows crank * bn/2 ...) of every tap's tile
     const int bt = tid - 32;
     int s = 0; uint32_t ph = 0;
-    int pending = 0, oldest = 0;
+    int pending = 0, oldest = 0, tl = 0, ta = 0;
+    // committed weight tiles a loader thread runs ahead of its completion signal.  One: the 16-byte LDGSTS path moves ~23 B/clk per SM however
+    // many are queued; with two ahead ConvT 128->64 went from 55 to 70 us, with five the landing time of a tile went from ~1400 to ~9000 clk
+    // (profiles/r02e_trace_halo.txt, r02e_sweep_cfgs.txt) -- deeper is slower, not faster.
+    const int depth = min(SB - 1, p.b_depth);
     const uint32_t pieces = (uint32_t)(p.bn / 2) * 8u;
     uint32_t full_addr[kMaxStages];
     for (int i = 0; i < kMaxStages; ++i) full_addr[i] = mapa_u32(smem_u32(&hdr->full[i]), 0);
@@ -880,15 +1115,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
             const int kc = halo_tap(p, grp, t4) * cchunks + cc;
             const char* bsrc = bcls + (size_t)kc * p.n_pad * 128;
             mbar_wait_cluster(&hdr->empty[s], ph ^ 1, p.err);
+            if (bt == 0) tr(tron, 1, tl++);
             const uint32_t b_dst = smem_u32(bst0 + (size_t)s * b_half_bytes);
             for (uint32_t i = (uint32_t)bt; i < pieces; i += kBLoaderThreads) cp_async16(b_dst + i * 16u, bsrc + (size_t)i * 16u, 16u);
             cp_async_commit();
-            if (++pending > 1) {
+            if (++pending > depth) {
               // the 96 loader threads meet on a named barrier and ONE of them arrives at the leader: 192 cluster-scope arrivals per
               // tap on a single mbarrier (half of them remote) serialised the pair to half the single-CTA rate
-              cp_async_wait<1>(); fence_proxy_async();
+              cp_async_wait_dyn(depth); fence_proxy_async();
               asm volatile("bar.sync 2, 96;" ::: "memory");
-              if (bt == 0) mbar_arrive_cluster(full_addr[oldest]);
+              if (bt == 0) { mbar_arrive_cluster(full_addr[oldest]); tr(tron, 2, ta++); }
               if (++oldest == SB) oldest = 0;
               --pending;
             }
@@ -896,7 +1132,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
           }
     }
     while (pending > 0) {
-      cp_async_wait<0>(); fence_proxy_async();
+      cp_async_wait_dyn(pending - 1); fence_proxy_async();
       asm volatile("bar.sync 2, 96;" ::: "memory");
       if (bt == 0) mbar_arrive_cluster(full_addr[oldest]);
       if (++oldest == SB) oldest = 0;
@@ -906,39 +1142,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
     // ================================================================ MMA issuer: one elected thread of the LEADER CTA
     if (leader && elect_one()) {
       const uint32_t idesc = umma_idesc(256, p.bn, false, false);
+      const uint32_t a_hi = (uint32_t)(umma_desc(0, 16, 9 * 128) >> 32), b_hi = (uint32_t)(umma_desc(0, 16, 1024) >> 32);
+      const uint32_t a_lbo = (16u >> 4) << 16;
+      const int mt_ = p.mt; const uint32_t acc_slot_ = (uint32_t)p.acc_slot;
       int s = 0; uint32_t ph = 0; int it = 0;
-      int bi = 0; uint32_t bph = 0;
+      int bi = 0; uint32_t bph = 0; int tb = 0, tt = 0;
       for (long long w = w0; w < p.work_total; w += wstep, ++it) {
         const int ab = (p.acc_bufs == 2) ? (it & 1) : 0;
         const uint32_t aph = (uint32_t)((it / p.acc_bufs) & 1);
         mbar_wait_cluster(&hdr->accempty[ab], aph ^ 1, p.err);
+      tr(tron, 7, 2);
         tc_fence_after();
         bool first = true;
         for (int grp = 0; grp < ngroups; ++grp)
           for (int cc = 0; cc < cchunks; ++cc) {
             mbar_wait_cluster(&hdr->blk_full[bi], bph, p.err);
+          tr(tron, 3, tb++);
             const uint32_t blk = smem_u32(blk0 + (size_t)bi * p.blk_bytes);
             for (int t4 = 0; t4 < 4; ++t4) {
               const int qz = t4 >> 1, qx = t4 & 1;
               mbar_wait_cluster(&hdr->full[s], ph, p.err);
+            tr(tron, 4, tt);
               tc_fence_after();
               const uint32_t b_base = smem_u32(bst0 + (size_t)s * b_half_bytes);
-              for (int sub = 0; sub < p.mt; ++sub) {
-                const uint32_t d_addr = tmem_base + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
-                const uint32_t a_view = blk + (uint32_t)(((sub * 2 + qz) * 8) * 9 + qx) * 128u;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint64_t da = umma_desc(a_view + kk * 32, 16, 9 * 128);
-                  const uint64_t db = umma_desc(b_base + kk * 32, 16, 1024);
-                  umma2_bf16(d_addr, da, db, idesc, (first && kk == 0) ? 0u : 1u);
-                }
-              }
+              halo_issue_tap<true>(tmem_base + (uint32_t)(ab * mt_ * acc_slot_), acc_slot_, mt_,
+                                   (((blk & 0x3FFFFu) >> 4) + (uint32_t)((qz * 72 + qx) * 8)) | a_lbo, ((b_base & 0x3FFFFu) >> 4) | a_lbo, a_hi, b_hi, idesc, first);
               first = false;
               umma2_commit(&hdr->empty[s]);
+            tr(tron, 5, tt++);
               if (++s == SB) { s = 0; ph ^= 1; }
             }
             umma2_commit(&hdr->blk_empty[bi]);
-            if (++bi == 2) { bi = 0; bph ^= 1; }
+            if (++bi == p.a_blocks) { bi = 0; bph ^= 1; }
           }
         umma2_commit(&hdr->accfull[ab]);
       }
@@ -955,6 +1190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
   // neither CTA may leave while the other can still touch its shared memory, barriers or tensor memory
   tc_fence_before();
   cluster_sync_all();
+  if (tid == 0) tr(tron, 7, 3);
   if (warp == 4) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
 }
 
@@ -1111,6 +1347,26 @@ static int igemm_tiles(const sg_igemm_args* a, bool ws_ok, TileCfg* t) {
   return 0;
 }
 
+// Shared-memory plan of the halo kernels: [header][a_blocks halo blocks][b_stages weight tiles][epilogue staging tile].
+// Preference order (measured, profiles/r02e_trace_halo.txt): the staging tile (the direct tile store cost 18 % of the kernel), then a third
+// halo block (a 46 KB block takes ~3400 clk to land, exactly the time its predecessor is consumed in: two blocks left the MMA thread
+// waiting ~330 clk per block), as long as at least 4 weight stages remain.  Returns the dynamic shared memory size.
+static size_t halo_smem_plan(IgemmP& p, unsigned b_tile, bool bf16_out) {
+  const long long total = 227LL * 1024 - kSmemHeader;
+  const char* ns = getenv("SG_B200_NO_EPI_STAGE");
+  unsigned epi = (bf16_out && p.planes == 1 && (p.bn == 64 || p.bn == 128) && !(ns && ns[0] == '1')) ? 128u * (unsigned)p.bn * 2u : 0u;
+  int blocks = 3;
+  { const char* ab = getenv("SG_B200_HALO_BLOCKS"); if (ab && atoi(ab) == 2) blocks = 2; }
+  if (blocks == 3 && (total - 3LL * p.blk_bytes - epi) / b_tile < 4) blocks = 2;
+  if ((total - (long long)blocks * p.blk_bytes - epi) / b_tile < 3) epi = 0;
+  p.a_blocks = blocks;
+  p.b_stages = (int)std::min<long long>(kMaxStages, (total - (long long)blocks * p.blk_bytes - epi) / b_tile);
+  if (p.b_stages < 0) p.b_stages = 0;
+  const size_t used = kSmemHeader + (size_t)blocks * p.blk_bytes + (size_t)p.b_stages * b_tile;
+  p.epi_off = epi ? (unsigned)used : 0u;
+  return used + epi;
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -1177,7 +1433,19 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   int stages = (int)(budget / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return sg_fail(-23, "sg_igemm: tile does not fit shared memory");
+  // epilogue staging tile behind the stages (see epilogue_role): worth a stage where the output is the larger stream (bn <= 128)
+  unsigned plain_epi = 0;
+  {
+    const char* ns = getenv("SG_B200_NO_EPI_STAGE");
+    if (a->out_kind == SG_OUT_BF16 && !split_ws && a->planes == 1 && (bn == 64 || bn == 128) && !(ns && ns[0] == '1')) {
+      const unsigned epi = 128u * (unsigned)bn * 2u;
+      int st2 = budget > epi ? (int)((budget - epi) / p.stage_bytes) : 0;
+      if (st2 > kMaxStages) st2 = kMaxStages;
+      if (st2 >= std::min(stages, 4)) { stages = st2; plain_epi = epi; }
+    }
+  }
   p.stages = stages;
+  p.epi_off = plain_epi ? (unsigned)(kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes) : 0u;
   // ---- TMA gather: the whole A tile of a (tap, 64-channel) chunk is one tensor-map box
   p.use_tma = 0;
   {
@@ -1220,12 +1488,18 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     }
   }
   { const char* dg = getenv("SG_B200_IGEMM_DIAG"); p.diag = dg ? atoi(dg) : 0; }
+  // weight tiles through the TMA unit: the CTA-pair halo kernel at bn >= 128 only (there the weights are the larger stream and the
+  // LSU path's ~23 B/clk per SM starved the MMAs: 45 -> 40 us on Conv3d 64->128).  Everywhere else it measured slower -- narrow tiles
+  // (ConvT 128->64: the TMA unit is busy with the halo blocks), the single-CTA halo kernel and the plain kernel (Conv3d 128->256
+  // 39.9 -> 42.0 us): profiles/r02e_sweep_cfgs.txt.  SG_B200_B_TMA=0/1 forces it for measurements.
+  { const char* e = getenv("SG_B200_B_TMA"); p.b_tma = e ? (e[0] != '0') : 0; }
+  { const char* e = getenv("SG_B200_B_DEPTH"); p.b_depth = e ? std::max(1, atoi(e)) : 1; }
   // ---- halo-reuse variant (see sg_igemm_halo_kernel): 8 x 8 x gz row grids, bf16
   {
     const bool conv = a->mode == SG_MODE_CONV;
     const char* no_halo = getenv("SG_B200_NO_HALO");
     if (p.use_tma && !(no_halo && no_halo[0] == '1') && a->planes == 1 && (conv || a->mode == SG_MODE_CONVT) && p.gx == 8 && p.gy == 8 &&
-        p.bx == 8 && p.by == 8 && is_pow2(p.gz) && p.gz % (2 * mt) == 0 && ksplit == 1 && (a->a.c % 64) == 0 && !p.diag) {
+        p.bx == 8 && p.by == 8 && is_pow2(p.gz) && p.gz % (2 * mt) == 0 && ksplit == 1 && (a->a.c % 64) == 0 && (p.diag == 0 || p.diag == 128)) {
       const uint64_t C = (uint64_t)a->a.c, W = (uint64_t)a->a.w, H = (uint64_t)a->a.h, D = (uint64_t)a->a.d;
       uint64_t dims[5] = {C, W, H, D, (uint64_t)a->a.n};
       uint64_t str[4] = {C * 2, W * C * 2, H * W * C * 2, D * H * W * C * 2};
@@ -1234,9 +1508,7 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
       uint32_t box[5] = {64, m * 9, m * 8, m * zp, 1};
       uint32_t es[5] = {1, m, m, m, 1};
       p.blk_bytes = 9u * 8u * zp * 128u;
-      const unsigned b_tile = (unsigned)bn * 128u;
-      const long long room = 227LL * 1024 - kSmemHeader - 2LL * p.blk_bytes;
-      p.b_stages = (int)std::min<long long>(kMaxStages, room / b_tile);
+      halo_smem_plan(p, (unsigned)bn * 128u, a->out_kind == SG_OUT_BF16 && !split_ws);
       if (p.b_stages >= 3 && tma_make_map(&p.tmH, a->a.ptr, 5, dims, str, box, es)) p.halo = 1;
     }
   }
@@ -1249,9 +1521,16 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
       q.pair = 1;
       q.m_tiles = p.m_tiles / 2;
       q.work_total = (long long)q.classes * q.n_tiles * q.m_tiles;
-      const long long room = 227LL * 1024 - kSmemHeader - 2LL * q.blk_bytes;
-      q.b_stages = (int)std::min<long long>(kMaxStages, room / ((long long)(bn / 2) * 128));
-      const size_t psmem = kSmemHeader + 2 * (size_t)q.blk_bytes + (size_t)q.b_stages * (size_t)(bn / 2) * 128;
+      { const char* e = getenv("SG_B200_B_TMA"); q.b_tma = e ? (e[0] != '0') : (bn >= 128); }
+      const size_t psmem = halo_smem_plan(q, (unsigned)(bn / 2) * 128u, a->out_kind == SG_OUT_BF16 && !split_ws);
+      if (q.b_tma) {
+        const uint64_t brows = (uint64_t)q.classes * (uint64_t)q.kchunks * (uint64_t)q.n_pad;
+        uint64_t bd[2] = {64, brows};
+        uint64_t bs[1] = {128};
+        uint32_t bb[2] = {64, (uint32_t)(bn / 2)};
+        uint32_t be[2] = {1, 1};
+        if (brows >= (1ull << 31) || !tma_make_map(&q.tmB, a->b_packed, 2, bd, bs, bb, be, false)) q.b_tma = 0;
+      }
       static bool pattr_set = false;
       if (!pattr_set) {
         cudaError_t e = cudaFuncSetAttribute(sg_igemm_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1267,7 +1546,7 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     }
   }
   if (p.halo) {
-    const size_t hsmem = kSmemHeader + 2 * (size_t)p.blk_bytes + (size_t)p.b_stages * (size_t)bn * 128;
+    const size_t hsmem = halo_smem_plan(p, (unsigned)bn * 128u, a->out_kind == SG_OUT_BF16 && !split_ws);
     static bool hattr_set = false;
     if (!hattr_set) {
       cudaError_t e = cudaFuncSetAttribute(sg_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1281,7 +1560,8 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     sg_count_launch();
     return 0;
   }
-  const size_t smem = kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes;
+  p.epi_off = plain_epi ? (unsigned)(kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes) : 0u;      // (the halo plans above overwrote it)
+  const size_t smem = kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes + plain_epi;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sg_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

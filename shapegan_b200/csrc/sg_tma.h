@@ -31,7 +31,7 @@ inline EncodeTiledFn tma_encode_fn() {
 
 // bf16 tensor map with 128B swizzle.  dims/box/estr are innermost-first; strides_bytes has rank-1 entries (dims 1..).
 inline bool tma_make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                         const uint32_t* box, const uint32_t* estr) {
+                         const uint32_t* box, const uint32_t* estr, bool swizzle = true) {
   EncodeTiledFn fn = tma_encode_fn();
   if (!fn) return false;
   cuuint64_t gd[5], gs[4];
@@ -39,7 +39,7 @@ inline bool tma_make_map(CUtensorMap* m, const void* base, int rank, const uint6
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estr[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -81,6 +81,12 @@ __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap*
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
       "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(mbar)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar) {
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(bar) & 0xFEFFFFFFu;
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(m), "r"(c0), "r"(c1), "r"(mbar)
+               : "memory");
 }
 // shared -> global tile store (bulk async-group completion): the box is read from 128B-swizzled shared memory
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {

@@ -525,7 +525,11 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
   }
   const int sms = sg_num_sms();
   const char* no_pair = getenv("SG_B200_NO_WGRAD_PAIR");
-  if (p.use_tma && (p.m_tiles & 1) == 0 && !(no_pair && no_pair[0] == '1')) {
+  // measured (profiles/r02e_sweep_wgrad_pair.txt): +3 % on the SDFNet layers (M = 512, millions of rows), -3 % on Conv3d(128->256) at B = 64
+  // (4096 rows per split: the cluster launch and the two extra cluster barriers are not amortised) -> long contractions only
+  long long pair_min_rows = 1LL << 18;
+  { const char* mr = getenv("SG_B200_WGRAD_PAIR_MIN_ROWS"); if (mr) pair_min_rows = atoll(mr); }      // tests force the pair on small problems
+  if (p.use_tma && (p.m_tiles & 1) == 0 && a->rows >= pair_min_rows && !(no_pair && no_pair[0] == '1')) {
     p.pair = 1;
     p.work_total = (long long)(p.m_tiles / 2) * p.n_groups * p.ksplit;            // in pairs
     cudaLaunchConfig_t cfg;

@@ -312,6 +312,7 @@ def test_wgrad_cta_pair_multicast(planes, monkeypatch):
     with more than one work item per pair and a ragged row count."""
     L, raw = _imports()
     res = []
+    monkeypatch.setenv('SG_B200_WGRAD_PAIR_MIN_ROWS', '0')       # the launcher keeps pairs for long contractions only
     for no_pair in ('0', '1'):
         monkeypatch.setenv('SG_B200_NO_WGRAD_PAIR', no_pair)
         out = []

@@ -45,6 +45,15 @@ def convt_fwd(B, r, cin, cout):          # also == conv dgrad with roles swapped
     return lambda bn, mt, ks: raw.igemm(L.MODE_CONVT, 1, x, (B, r, r, r, cin), B * r ** 3, 8 * cin, img, cout, y, cout, out_dims=(ro, ro, ro), bn=bn, mt=mt, ksplit=ks), fl
 
 
+def patch_fwd(B, r, cout, masked):       # Conv3d(1 -> cout) on the fp32 input volume (D1 forward; masked + in place = the adjoint sweep's first layer)
+    x = torch.randn((B, r, r, r), device='cuda'); w = torch.randn((cout, 1, 4, 4, 4), device='cuda') * 0.05
+    img = raw.pack_b(w, 1, cout, 64, 64, 1, 1, s_n0=64, s_tap=1, s_c=0); ro = r // 2; rows = B * ro ** 3
+    y = bf((rows, cout))
+    fl = 2.0 * rows * cout * 64
+    kw = dict(mask=y, mask_act=L.ACT_LRELU) if masked else dict(act=L.ACT_LRELU)
+    return lambda bn, mt, ks: raw.igemm(L.MODE_PATCH, 1, x, (B, r, r, r, 1), rows, 64, img, cout, y, cout, bn=bn, mt=mt, ksplit=ks, **kw), fl
+
+
 def wgrad_conv(B, r, cin, cout):
     x = bf((B, r, r, r, cin)); ro = r // 2; dy = bf((B, ro, ro, ro, cout)); rows = B * ro ** 3
     g = torch.zeros((cout, cin, 4, 4, 4), device='cuda')
@@ -53,8 +62,9 @@ def wgrad_conv(B, r, cin, cout):
 
 
 print('torch', torch.__version__, torch.cuda.get_device_name(0))
-for B in (64, 128):
-    layers = [('conv 64->128 16^3 (D2 fwd / G3 dgrad)', conv_fwd(B, 16, 64, 128)), ('conv 128->256 8^3 (D3 fwd / G2 dgrad)', conv_fwd(B, 8, 128, 256)),
+for B in (64, 128, 192):
+    layers = [('patch conv 1->64 32^3 (D1 fwd)', patch_fwd(B, 32, 64, False)), ('patch conv 1->64 32^3 masked in place (D1 adjoint)', patch_fwd(B, 32, 64, True)),
+              ('conv 64->128 16^3 (D2 fwd / G3 dgrad)', conv_fwd(B, 16, 64, 128)), ('conv 128->256 8^3 (D3 fwd / G2 dgrad)', conv_fwd(B, 8, 128, 256)),
               ('convT 256->128 4^3 (G2 fwd / D3 dgrad)', convt_fwd(B, 4, 256, 128)), ('convT 128->64 8^3 (G3 fwd / D2 dgrad)', convt_fwd(B, 8, 128, 64)),
               ('wgrad conv 64->128 16^3 (D2 / G3)', wgrad_conv(B, 16, 64, 128)), ('wgrad conv 128->256 8^3 (D3 / G2)', wgrad_conv(B, 8, 128, 256))]
     for name, (fn, fl) in layers:
@@ -63,6 +73,6 @@ for B in (64, 128):
                 continue
             try:
                 us = timeit(lambda: fn(bn, mt, ks))
-                print('B=%3d %-42s %6.2f GFLOP  bn=%3d mt=%d ks=%d  %8.1f us  %7.1f TFLOP/s' % (B, name, fl / 1e9, bn, mt, ks, us, fl / us / 1e6))
+                print('B=%3d %-50s %6.2f GFLOP  bn=%3d mt=%d ks=%d  %8.1f us  %7.1f TFLOP/s' % (B, name, fl / 1e9, bn, mt, ks, us, fl / us / 1e6))
             except Exception as e:
-                print('B=%3d %-42s bn=%3d mt=%d ks=%d -- %s' % (B, name, bn, mt, ks, str(e)[:80]))
+                print('B=%3d %-50s bn=%3d mt=%d ks=%d -- %s' % (B, name, bn, mt, ks, str(e)[:80]))
