@@ -376,24 +376,23 @@ __device__ __forceinline__ void patch_store8(const float (&f)[2][20], int g, uin
 
 // activations used on the path
 enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+// `act` is uniform over a launch.  The piecewise-linear activations (everything on the training path except the generator's tanh and
+// the GAN discriminator's sigmoid) are written as selects on loop-invariant predicates, not as a switch: inside the unrolled 8-element
+// loops of the HBM-bound kernels and the GEMM epilogues a switch cost ~19 instructions per element (profiles/r02e_ncu_patch.txt).
 __device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case ACT_LRELU: return v > 0.f ? v : v * kLreluSlope;
-    case ACT_RELU: return v > 0.f ? v : 0.f;
-    case ACT_TANH: return tanhf(v);
-    case ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-    default: return v;
+  if (act <= ACT_RELU) {
+    const float neg = (act == ACT_LRELU) ? v * kLreluSlope : 0.f;
+    return (act == ACT_NONE || v > 0.f) ? v : neg;
   }
+  return act == ACT_TANH ? tanhf(v) : 1.f / (1.f + __expf(-v));
 }
 // derivative expressed through the stored OUTPUT y of the activation
 __device__ __forceinline__ float act_grad_from_output(float y, int act) {
-  switch (act) {
-    case ACT_LRELU: return y > 0.f ? 1.f : kLreluSlope;
-    case ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case ACT_TANH: return 1.f - y * y;
-    case ACT_SIGMOID: return y * (1.f - y);
-    default: return 1.f;
+  if (act <= ACT_RELU) {
+    const float neg = (act == ACT_LRELU) ? kLreluSlope : 0.f;
+    return (act == ACT_NONE || y > 0.f) ? 1.f : neg;
   }
+  return act == ACT_TANH ? 1.f - y * y : y * (1.f - y);
 }
 
 }  // namespace sg

@@ -1315,10 +1315,22 @@ static int igemm_tiles(const sg_igemm_args* a, bool ws_ok, TileCfg* t) {
     const long long items = row_tiles * classes * (a->n_pad / bn);
     const char* nsk = getenv("SG_B200_NO_SPLITK");
     const bool no_split = nsk && nsk[0] == '1';
-    if (ksplit <= 0 && ws_ok && !no_split && a->out_kind != SG_OUT_F32_ATOMIC && items * 2 <= sms && kchunks >= 32 && (bn & 31) == 0) {
-      int ks = (int)(sms / items);
-      while (ks > 1 && kchunks / ks < 16) --ks;
-      if (ks > 1) { ksplit = ks; auto_split = true; }
+    if (ksplit <= 0 && ws_ok && !no_split && a->out_kind != SG_OUT_F32_ATOMIC && items < sms && kchunks >= 32 && (bn & 31) == 0) {
+      // less than one wave of tiles and a long K: split K, and choose the number of M sub-tiles per CTA together with the split so that
+      // the machine is as full as possible (ties: fewer splits).  Conv3d(128->256) on the batched critic's 3 x 64 samples is 96 tiles:
+      // unsplit 96 CTAs ran 91 us, two sub-tiles x 3 splits = 144 CTAs run 66 us (profiles/r02e_sweep_d3_cfgs.txt).
+      int best_ks = 1, best_mt = 1; long long best_fill = 0;
+      for (int mtc = 1; mtc <= ((mt <= 0) ? 2 : 1); ++mtc) {
+        const int m_try = (mt > 0) ? mt : mtc;
+        if (m_try * bn > 512) continue;
+        const long long it0 = ((row_tiles + m_try - 1) / m_try) * classes * (a->n_pad / bn);
+        if (it0 >= sms) continue;
+        int ks = (int)(sms / it0);
+        while (ks > 1 && kchunks / ks < 16) --ks;
+        const long long fill = it0 * ks;
+        if (fill > best_fill || (fill == best_fill && ks < best_ks)) { best_fill = fill; best_ks = ks; best_mt = m_try; }
+      }
+      if (best_ks > 1) { ksplit = best_ks; if (mt <= 0) mt = best_mt; auto_split = true; }
     }
     // not enough work for the machine: narrow the N tile (keeps tensor throughput, multiplies CTAs)
     if (!auto_split)

@@ -399,7 +399,15 @@ __global__ void sg_wgrad_reduce_kernel(const sg_wgrad_reduce_args a) {
     const int tap = n / a.cb, c = n - tap * a.cb;
     if (a.c_valid > 0 && c >= a.c_valid) continue;
     float acc = 0.f;
-    for (int s = 0; s < a.ksplit; ++s) acc += a.partials[((size_t)s * a.m_pad + m) * n_total + n];
+    const float* p = a.partials + (size_t)m * n_total + n;
+    const size_t sstride = (size_t)a.m_pad * n_total;
+    for (int s0 = 0; s0 < a.ksplit; s0 += 8) {        // eight loads in flight, added in split order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (s0 + u < a.ksplit) ? p[(size_t)(s0 + u) * sstride] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
     float* g = a.grad + (long long)m * a.sm + (long long)tap * a.st + (long long)c * a.sc;
     acc *= a.scale;
     *g = a.accumulate ? (*g + acc) : acc;
@@ -565,7 +573,16 @@ __global__ void sg_wgrad_reduce_t64_kernel(const sg_wgrad_reduce_args a) {
     const int c = c0 + lane;
     if (c < a.cb) {
       const float* p = a.partials + (size_t)m * n_total + (size_t)tap * a.cb + c;
-      for (int s = 0; s < a.ksplit; ++s) acc += p[(size_t)s * a.m_pad * n_total];
+      // eight splits in flight per round, added in split order (a rolled `acc += p[...]` loop waits out every load's latency in turn:
+      // 8 taps x 9 splits x ~600 clk = 23 us per launch for 19 MB -- profiles/r02c_launches_launches_wgan_gp.txt)
+      const size_t sstride = (size_t)a.m_pad * n_total;
+      for (int s0 = 0; s0 < a.ksplit; s0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (s0 + u < a.ksplit) ? p[(size_t)(s0 + u) * sstride] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
     }
     tile[lane][tap] = acc * a.scale;
   }

@@ -13,6 +13,7 @@ with the LeakyReLU masks held fixed.
 
 Tensors between layers are NDHWC bf16 plane tensors [P, B, D, H, W, C] (P = 1 bf16, P = 2 hi/lo fp32x);
 single-channel voxel volumes at module boundaries are fp32 [B, D, H, W]."""
+import os
 import weakref
 
 import torch
@@ -27,6 +28,10 @@ r64 = lambda v: raw.round_up(v, 64)   # noqa: E731
 
 
 # ------------------------------------------------------------------------------------------------- packed-weight cache
+# measurement only (results are WRONG): never re-pack a weight once packed -- the step-time difference is the cost of the per-step re-packs
+_STALE_PACK = os.environ.get('SG_B200_DIAG_STALE_PACK') == '1'
+
+
 class _PackCache:
     """fp32 parameter -> tensor-core operand image, cached per parameter OBJECT (a uid stamped on the tensor; a
     device address can be recycled by the caching allocator, so it is not an identity) and validated by
@@ -59,7 +64,7 @@ class _PackCache:
     def lookup(self, key, sig):
         """cached payload for `key` if it was built from `sig` in the current capture context, else None"""
         hit = self.store.get(key)
-        if hit is not None and hit[0] == sig and hit[2] == raw.capture_id():
+        if hit is not None and (_STALE_PACK or (hit[0] == sig and hit[2] == raw.capture_id())):
             return hit[1]
         return None
 

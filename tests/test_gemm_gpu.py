@@ -337,3 +337,22 @@ def test_wgrad_cta_pair_multicast(planes, monkeypatch):
     for a, c in zip(res[0], res[1]):
         assert torch.equal(a, c), 'the pair kernel must reproduce the single-CTA partial sums bit for bit (same MMAs, same order)'
     check_error_word()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('planes', [1, 2])
+def test_fast_weight_pack_is_bit_identical(planes, monkeypatch):
+    """sg_pack_b's shared-memory-transposing kernel for the conv layouts (64 contiguous taps per (n, c) pair) writes exactly the bytes
+    of the generic strided kernel: Conv3d fwd / dgrad, ConvTranspose3d fwd / dgrad images, ragged N (cout = 72 -> n_pad = 80)."""
+    L, raw = _imports()
+    packers = [('conv_fwd', raw.pack_conv_fwd, (72, 128, 4, 4, 4)), ('conv_dgrad', raw.pack_conv_dgrad, (128, 64, 4, 4, 4)),
+               ('convt_fwd', raw.pack_convt_fwd, (128, 72, 4, 4, 4)), ('convt_dgrad', raw.pack_convt_dgrad, (64, 128, 4, 4, 4))]
+    for name, fn, shape in packers:
+        w = rnd(shape, 11)
+        monkeypatch.setenv('SG_B200_NO_FAST_PACK', '1')
+        ref = fn(w, planes).clone()
+        monkeypatch.setenv('SG_B200_NO_FAST_PACK', '0')
+        got = fn(w, planes)
+        assert ref.numel() == got.numel() and torch.equal(ref, got), name
+    monkeypatch.delenv('SG_B200_NO_FAST_PACK')
+    check_error_word()

@@ -32,5 +32,13 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sg_igemm -s 3 -c 1 -f -o gpurun_out/prof_conv python tools/prof_conv.py 5 > gpurun_out/ncu_conv.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sg_sdfnet_fwd -s 2 -c 1 -f -o gpurun_out/prof_sdf python tools/prof_sdf_fwd.py > gpurun_out/ncu_sdf.log 2>&1
 timeout 300 python tools/sweep_layers.py > gpurun_out/sweep.txt 2>&1
+for tool in racecheck synccheck; do
+  timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_igemm.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a gpurun_out/times.log; tail -4 gpurun_out/sanitizer_$tool.log
+done
+# clock traces need the instrumented build: last, the box is discarded afterwards
+timeout 600 python -m shapegan_b200.build --force --trace > /dev/null 2>&1
+SG_B200_NO_REBUILD=1 timeout 300 python tools/trace_igemm.py > gpurun_out/trace_conv.txt 2>&1
+SG_B200_NO_REBUILD=1 timeout 300 python tools/trace_igemm.py convt > gpurun_out/trace_convt.txt 2>&1
+SG_B200_NO_REBUILD=1 timeout 300 python tools/trace_igemm.py patch > gpurun_out/trace_patch.txt 2>&1
 fi
 echo "done $(( $(date +%s)-T0 ))s" | tee -a gpurun_out/times.log
