@@ -109,6 +109,17 @@ __device__ __forceinline__ void mask_mul8(float* v, const uint4& m, int mask_act
   }
 }
 
+// this warp's 32 rows x 8 chunks (bn = 64) of the mask tile, coalesced: lane i + 32 k reads chunk (i & 7) of row (i >> 3) + 4 k
+__device__ __forceinline__ void mask_tile_load8(const bf16* mask, long long my_ob, int lane, uint4 (&m)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = lane + 32 * k, rr = i >> 3, ch = i & 7;
+    const long long ob = __shfl_sync(0xffffffffu, my_ob, rr);
+    m[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (ob >= 0) m[k] = *reinterpret_cast<const uint4*>(mask + ob + ch * 8);      // plain load: `mask` may alias `out`
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_t(float v, int runtime_act) {
   if (ACT == ACT_NONE) return v;
@@ -127,6 +138,33 @@ struct EpiP {   // the fields the epilogue needs, copied ONCE into registers: th
   unsigned epi_off;
   const float* bias; const bf16* mask; char* out; int* err;
 };
+
+// 32 accumulator columns of this lane's row -> (+ bias) -> activation -> (x act'(mask), read from the staging slot) -> bf16 -> staging slot
+template <int ACT, bool MASKED>
+__device__ __forceinline__ void staged_convert32(const uint32_t (&r)[32], const float* sb, bool add_bias, int act, int mask_act, uint32_t srow, int cb,
+                                                 int lane) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = add_bias ? *reinterpret_cast<const float4*>(sb + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[j] = act_t<ACT>(__uint_as_float(r[j]) + b.x, act);
+    v[j + 1] = act_t<ACT>(__uint_as_float(r[j + 1]) + b.y, act);
+    v[j + 2] = act_t<ACT>(__uint_as_float(r[j + 2]) + b.z, act);
+    v[j + 3] = act_t<ACT>(__uint_as_float(r[j + 3]) + b.w, act);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const uint32_t slot = srow + (uint32_t)((((cb + j) >> 3) ^ (lane & 7)) << 4);
+    if (MASKED) {
+      const uint4 m = ld_shared_v4(slot);
+      mask_mul8(v + j, m, mask_act);
+    }
+    uint4 hi;
+    hi.x = pack_bf16x2(v[j], v[j + 1]); hi.y = pack_bf16x2(v[j + 2], v[j + 3]);
+    hi.z = pack_bf16x2(v[j + 4], v[j + 5]); hi.w = pack_bf16x2(v[j + 6], v[j + 7]);
+    st_shared_v4(slot, hi);
+  }
+}
 
 template <int ACT>
 __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, uint32_t tmem_base, int cps) {
@@ -163,25 +201,41 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
       asm volatile("bar.sync 1, 128;" ::: "memory");
       staged_nt = nt;
     }
-    if (p.pair) mbar_wait_cluster(&hdr->accfull[ab], aph, p.err); else mbar_wait(&hdr->accfull[ab], aph, p.err);
-    tc_fence_after();
-    if (etid == 0) tr((gp.diag & 128) && blockIdx.x == 0, 6, 2 * it);
     const bool tile_full = (nt * p.bn + p.bn <= p.n_valid);
     const bool fast = tile_full && (p.bn & 31) == 0 &&
                       ((p.out_kind == SG_OUT_BF16 && (p.out_ld & 7) == 0) || (p.out_kind == SG_OUT_F32 && (p.out_ld & 3) == 0 && p.mask == nullptr));
     const bool staged = fast && p.epi_off != 0u && p.out_kind == SG_OUT_BF16 && p.planes == 1 && (p.bn == 64 || p.bn == 128);
-    for (int sub = 0; sub < p.mt; ++sub) {
-      const long long gr = ((long long)mtile * p.mt + sub) * kTileRows + trow;
-      const bool valid = gr < p.rows;
-      long long orow = gr;
-      if (p.mode == SG_MODE_CONVT && valid) {
-        int qw = (int)(gr % p.aW); long long t = gr / p.aW;
-        int qh = (int)(t % p.aH); t /= p.aH;
-        int qd = (int)(t % p.aD); long long n = t / p.aD;
-        orow = ((n * p.oD + 2 * qd + ((cls >> 2) & 1)) * p.oH + 2 * qh + ((cls >> 1) & 1)) * p.oW + 2 * qw + (cls & 1);
+    // this lane's output row (element offset of its first column, -1 = beyond the last row) in each sub-tile
+    long long ob_sub[2] = {-1, -1};
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      if (sub < p.mt) {
+        const long long gr = ((long long)mtile * p.mt + sub) * kTileRows + trow;
+        if (gr < p.rows) {
+          long long orow = gr;
+          if (p.mode == SG_MODE_CONVT) {
+            int qw = (int)(gr % p.aW); long long t = gr / p.aW;
+            int qh = (int)(t % p.aH); t /= p.aH;
+            int qd = (int)(t % p.aD); long long n = t / p.aD;
+            orow = ((n * p.oD + 2 * qd + ((cls >> 2) & 1)) * p.oH + 2 * qh + ((cls >> 1) & 1)) * p.oW + 2 * qw + (cls & 1);
+          }
+          ob_sub[sub] = orow * p.out_ld + (long long)nt * p.bn + (long long)ks * p.ks_stride;   // ks_stride: split-K partial slabs
+        }
       }
+    }
+    // bn = 64 (8 chunks per row): the mask tile of a sub-tile is fetched one phase ahead -- sub-tile 0's while this warp still waits for
+    // the accumulator, sub-tile 1's while sub-tile 0 is converted -- so the ~2 k clock round trip to HBM (the mask is a 100 MB activation
+    // of the batched critic) is never exposed.  (bn = 128 would need 64 registers for the tile in flight: loaded in phase, below.)
+    const bool mpref = staged && p.mask != nullptr && p.bn == 64;
+    uint4 mpre[8];
+    if (mpref) mask_tile_load8(p.mask, ob_sub[0], lane, mpre);
+    if (p.pair) mbar_wait_cluster(&hdr->accfull[ab], aph, p.err); else mbar_wait(&hdr->accfull[ab], aph, p.err);
+    tc_fence_after();
+    if (etid == 0) tr((gp.diag & 128) && blockIdx.x == 0, 6, 2 * it);
+    for (int sub = 0; sub < p.mt; ++sub) {
+      const bool valid = ob_sub[sub] >= 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * p.mt + sub) * p.acc_slot);
-      const long long obase = orow * p.out_ld + (long long)nt * p.bn + (long long)ks * p.ks_stride;   // ks_stride: split-K partial slabs
+      const long long obase = ob_sub[sub];
       if (staged) {
         // ---- staged stores.  A thread owns an accumulator ROW (TMEM lane), so direct stores put 16 bytes per lane at a row-pitch stride:
         // 32 half-written sectors per instruction; the tile store took 14.7 k clocks (profiles/r02e_trace_halo.txt).  Instead each warp
@@ -193,58 +247,53 @@ __device__ __noinline__ void epilogue_role(const IgemmP& gp, SmemHeader* hdr, ui
         const uint32_t srow = stg + (uint32_t)lane * pitch;
         const long long my_ob = valid ? obase : -1;
         __syncwarp();
-        if (p.mask != nullptr) {
+        if (mpref) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = lane + 32 * k, rr = i >> 3, ch = i & 7;
+            st_shared_v4(stg + (uint32_t)rr * pitch + (uint32_t)((ch ^ (rr & 7)) << 4), mpre[k]);
+          }
+          if (sub + 1 < p.mt) mask_tile_load8(p.mask, ob_sub[sub + 1], lane, mpre);
+          __syncwarp();
+        } else if (p.mask != nullptr) {
           // all of this warp's mask loads are issued before the first use (a rolled load -> store loop serialises the round trips:
           // 8 x ~2 k clocks per sub-tile made the masked D1 launch 3x slower than the unmasked one, profiles/r02e_trace_patch.txt)
-          uint4 mreg[16];
+          for (int k0 = 0; k0 < cpr; k0 += 8) {            // eight loads in flight per round (bn = 128: two rounds)
+            uint4 mreg[8];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            mreg[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (k < cpr) {
-              const int i = lane + 32 * k, rr = i >> lgc, ch = i & (cpr - 1);
+            for (int k = 0; k < 8; ++k) {
+              const int i = lane + 32 * (k0 + k), rr = i >> lgc, ch = i & (cpr - 1);
               const long long ob = __shfl_sync(0xffffffffu, my_ob, rr);
+              mreg[k] = make_uint4(0u, 0u, 0u, 0u);
               if (ob >= 0) mreg[k] = *reinterpret_cast<const uint4*>(p.mask + ob + ch * 8);      // plain load: `mask` may alias `out`
             }
-          }
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            if (k < cpr) {
-              const int i = lane + 32 * k, rr = i >> lgc, ch = i & (cpr - 1);
+            for (int k = 0; k < 8; ++k) {
+              const int i = lane + 32 * (k0 + k), rr = i >> lgc, ch = i & (cpr - 1);
               st_shared_v4(stg + (uint32_t)rr * pitch + (uint32_t)((ch ^ (rr & 7)) << 4), mreg[k]);
             }
           }
           __syncwarp();
         }
-        for (int c0 = 0; c0 < p.bn; c0 += 64) {        // bn = 64 or 128: two 32-column TMEM loads in flight per wait
-          uint32_t r[2][32];
-          __syncwarp();
-          tmem_ld32(t_addr + c0, r[0]);
-          tmem_ld32(t_addr + c0 + 32, r[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cb = c0 + 32 * h;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = add_bias ? *reinterpret_cast<const float4*>(sbias + cb + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              v[j] = act_t<ACT>(__uint_as_float(r[h][j]) + b.x, p.act);
-              v[j + 1] = act_t<ACT>(__uint_as_float(r[h][j + 1]) + b.y, p.act);
-              v[j + 2] = act_t<ACT>(__uint_as_float(r[h][j + 2]) + b.z, p.act);
-              v[j + 3] = act_t<ACT>(__uint_as_float(r[h][j + 3]) + b.w, p.act);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint32_t slot = srow + (uint32_t)((((cb + j) >> 3) ^ (lane & 7)) << 4);
-              if (p.mask != nullptr) {
-                const uint4 m = ld_shared_v4(slot);
-                mask_mul8(v + j, m, p.mask_act);
-              }
-              uint4 hi;
-              hi.x = pack_bf16x2(v[j], v[j + 1]); hi.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              hi.z = pack_bf16x2(v[j + 4], v[j + 5]); hi.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              st_shared_v4(slot, hi);
-            }
+        // accumulator -> bias / activation (/ mask) -> bf16 -> this lane's staging row.  Unmasked: two 32-column TMEM loads in flight per
+        // wait; masked: one (the mask tile in flight already holds 32 registers)
+        if (p.mask == nullptr) {
+          for (int c0 = 0; c0 < p.bn; c0 += 64) {
+            uint32_t r0[32], r1[32];
+            __syncwarp();
+            tmem_ld32(t_addr + c0, r0);
+            tmem_ld32(t_addr + c0 + 32, r1);
+            tmem_ld_wait();
+            staged_convert32<ACT, false>(r0, sbias + c0, add_bias, p.act, 0, srow, c0, lane);
+            staged_convert32<ACT, false>(r1, sbias + c0 + 32, add_bias, p.act, 0, srow, c0 + 32, lane);
+          }
+        } else {
+          for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            uint32_t r0[32];
+            __syncwarp();
+            tmem_ld32(t_addr + c0, r0);
+            tmem_ld_wait();
+            staged_convert32<ACT, true>(r0, sbias + c0, add_bias, p.act, p.mask_act, srow, c0, lane);
           }
         }
         __syncwarp();

@@ -356,3 +356,20 @@ def test_fast_weight_pack_is_bit_identical(planes, monkeypatch):
         assert ref.numel() == got.numel() and torch.equal(ref, got), name
     monkeypatch.delenv('SG_B200_NO_FAST_PACK')
     check_error_word()
+
+
+@pytest.mark.gpu
+def test_tiled_col2im_is_bit_identical(monkeypatch):
+    """second stage of ConvTranspose3d(C -> 1): the shared-memory tiled kernel sums the same 8 taps in the same order as the direct one
+    (16^3 -> 32^3 with bias + tanh = the generator's last layer; 8 x 4 x 12 grid without bias = an input-gradient shape)"""
+    L, raw = _imports()
+    for (n, d, h, w, act, with_bias) in ((3, 16, 16, 16, L.ACT_TANH, True), (2, 12, 4, 8, L.ACT_NONE, False)):
+        pm = rnd((n * d * h * w, 64), 5).to(torch.bfloat16).reshape(1, -1, 64)
+        bias = rnd((1,), 6) if with_bias else None
+        monkeypatch.setenv('SG_B200_NO_TILED_COL2IM', '1')
+        ref = raw.col2im_c1(pm, n, d, h, w, bias, act).clone()
+        monkeypatch.setenv('SG_B200_NO_TILED_COL2IM', '0')
+        got = raw.col2im_c1(pm, n, d, h, w, bias, act)
+        assert torch.equal(ref, got)
+    monkeypatch.delenv('SG_B200_NO_TILED_COL2IM')
+    check_error_word()
