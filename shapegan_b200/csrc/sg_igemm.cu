@@ -1549,10 +1549,10 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
     }
   }
   { const char* dg = getenv("SG_B200_IGEMM_DIAG"); p.diag = dg ? atoi(dg) : 0; }
-  // weight tiles through the TMA unit: the CTA-pair halo kernel at bn >= 128 only (there the weights are the larger stream and the
-  // LSU path's ~23 B/clk per SM starved the MMAs: 45 -> 40 us on Conv3d 64->128).  Everywhere else it measured slower -- narrow tiles
-  // (ConvT 128->64: the TMA unit is busy with the halo blocks), the single-CTA halo kernel and the plain kernel (Conv3d 128->256
-  // 39.9 -> 42.0 us): profiles/r02e_sweep_cfgs.txt.  SG_B200_B_TMA=0/1 forces it for measurements.
+  // weight tiles through the TMA unit: the CTA-pair halo kernel only.  There the LSU path's ~23 B/clk per SM (bn = 128) resp. its latency
+  // with two tiles in flight (bn = 64) starved the MMAs: Conv3d 64->128 45 -> 37 us, ConvT 128->64 61 -> 49 us at B = 64, 156 -> 121 us on
+  // the batched critic (profiles/r02e_sweep_btma.txt).  Everywhere else it measured slower -- the single-CTA halo kernel and the plain
+  // kernel (Conv3d 128->256 39.9 -> 42.0 us): profiles/r02e_sweep_cfgs*.txt.  SG_B200_B_TMA=0/1 forces it for measurements.
   { const char* e = getenv("SG_B200_B_TMA"); p.b_tma = e ? (e[0] != '0') : 0; }
   { const char* e = getenv("SG_B200_B_DEPTH"); p.b_depth = e ? std::max(1, atoi(e)) : 1; }
   // ---- halo-reuse variant (see sg_igemm_halo_kernel): 8 x 8 x gz row grids, bf16
@@ -1582,7 +1582,7 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
       q.pair = 1;
       q.m_tiles = p.m_tiles / 2;
       q.work_total = (long long)q.classes * q.n_tiles * q.m_tiles;
-      { const char* e = getenv("SG_B200_B_TMA"); q.b_tma = e ? (e[0] != '0') : (bn >= 128); }
+      { const char* e = getenv("SG_B200_B_TMA"); q.b_tma = e ? (e[0] != '0') : 1; }
       const size_t psmem = halo_smem_plan(q, (unsigned)(bn / 2) * 128u, a->out_kind == SG_OUT_BF16 && !split_ws);
       if (q.b_tma) {
         const uint64_t brows = (uint64_t)q.classes * (uint64_t)q.kchunks * (uint64_t)q.n_pad;

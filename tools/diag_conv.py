@@ -1,5 +1,5 @@
 """Which part of sg_igemm bounds a layer?  Times the kernel with parts switched off (SG_B200_IGEMM_DIAG bit mask:
-1 no A gather, 2 no B load, 4 no MMA, 8 no epilogue stores).  Results are garbage in those modes: timing only."""
+1 no A gather, 2 no B load, 4 no MMA, 8 no epilogue stores; any bit forces the plain kernel).  Results are garbage in those modes: timing only."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -50,18 +50,4 @@ for name, (fn, fl) in layers:
         print('   diag=%2d %-12s %8.1f us  %7.1f TFLOP/s-equivalent' % (d, what, us, fl / us / 1e6))
 os.environ['SG_B200_IGEMM_DIAG'] = '0'; os.environ['SG_B200_IGEMM_GRID'] = '0'
 
-# ---- per-iteration clock trace of CTA 0 (conv 64->128): where does a K-chunk iteration spend its time?
-import ctypes
-fn, _ = conv_fwd(16, 64, 128)
-for d, what, grid in ((128, 'full', 0), (128 + 15, 'nothing', 0), (128 + 3, 'no loads', 0), (128 + 4, 'no MMA', 0), (128 + 4, 'no MMA, 64 CTAs', 64), (128 + 4, 'no MMA, 32 CTAs', 32), (128 + 4, 'no MMA, 8 CTAs', 8), (128, 'full, 64 CTAs', 64)):
-    os.environ['SG_B200_IGEMM_DIAG'] = str(d); os.environ['SG_B200_IGEMM_GRID'] = str(grid)
-    fn(); torch.cuda.synchronize(); flush.zero_(); fn(); torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * 3072)()
-    L.check(L.lib().sg_debug_igemm_trace(buf, 3072), 'trace')
-    prod, got, iss = list(buf[0:64]), list(buf[1024:1088]), list(buf[2048:2112])
-    t0 = min(prod[0], got[0])
-    print('-- trace %s: iteration: producer-slot / mma-data / mma-issued (cycles since start), d(issue)' % what)
-    for i in range(64):
-        if i < 12 or i % 8 == 0 or i > 60:
-            print('   %2d  %7d %7d %7d   +%d' % (i, prod[i] - t0, got[i] - t0, iss[i] - t0, iss[i] - iss[i - 1] if i else 0))
-os.environ['SG_B200_IGEMM_DIAG'] = '0'; os.environ['SG_B200_IGEMM_GRID'] = '0'
+# (clock traces of CTA 0: tools/trace_igemm.py on a `python -m shapegan_b200.build --force --trace` build)
