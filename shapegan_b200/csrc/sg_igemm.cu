@@ -1080,7 +1080,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1) sg
   }
   if (warp == 4) tmem_alloc2(&hdr->tmem_base, 512);
   tc_fence_before();
-  cluster_sync_all();
+  __syncthreads();          // the allocator's shared-memory write vs this CTA's readers (compute-sanitizer racecheck does not take the cluster
+  cluster_sync_all();       // barrier below as a shared-memory synchronisation point: profiles/r02f_sanitizer.txt); then both CTAs are set up
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
   if (tid == 0) tr(tron, 7, 1);

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) sg_wgrad_kernel(const __grid_co
   }
   if (warp == 4) tmem_alloc(&hdr->tmem_base, 512);
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
   if ((smem_u32(smem) & 1023u) != 0) {

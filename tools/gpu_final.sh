@@ -32,6 +32,8 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sg_igemm -s 3 -c 1 -f -o gpurun_out/prof_conv python tools/prof_conv.py 5 > gpurun_out/ncu_conv.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sg_sdfnet_fwd -s 2 -c 1 -f -o gpurun_out/prof_sdf python tools/prof_sdf_fwd.py > gpurun_out/ncu_sdf.log 2>&1
 timeout 300 python tools/sweep_layers.py > gpurun_out/sweep.txt 2>&1
+timeout 300 python tools/prof_step.py wgan_gp > gpurun_out/step_kernels_wgan_gp.txt 2>/dev/null
+timeout 300 python tools/prof_step.py gan > gpurun_out/step_kernels_gan.txt 2>/dev/null
 for tool in racecheck synccheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_igemm.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a gpurun_out/times.log; tail -4 gpurun_out/sanitizer_$tool.log
 done
