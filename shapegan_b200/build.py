@@ -32,6 +32,20 @@ def build_lib(force=False, verbose=False, trace=False):
     if not force and not trace and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    # one builder at a time (torchrun starts N ranks that may all find the library stale): the others wait, then find it fresh
+    import fcntl
+    lock = open(os.path.join(LIB_DIR, '.build.lock'), 'w')
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not trace and not _stale():
+            return LIB_PATH
+        return _build_locked(verbose, trace)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose, trace):
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
     procs = []
@@ -49,11 +63,13 @@ def build_lib(force=False, verbose=False, trace=False):
         objs.append(obj)
     with open(os.path.join(objdir, 'ptxas.log'), 'w') as f:
         f.write('\n'.join(log))
-    cmd = [NVCC, '-shared', '-o', LIB_PATH] + objs + ['-lcudart']
+    tmp = LIB_PATH + '.tmp.%d' % os.getpid()
+    cmd = [NVCC, '-shared', '-o', tmp] + objs + ['-lcudart']
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:
         sys.stderr.write(out.stdout)
         raise RuntimeError('link failed')
+    os.replace(tmp, LIB_PATH)                      # atomic: a process that is loading the library never sees a half-written file
     if verbose:
         print('\n'.join(log))
     return LIB_PATH

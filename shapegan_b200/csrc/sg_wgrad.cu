@@ -569,23 +569,27 @@ __global__ void sg_wgrad_reduce_t64_kernel(const sg_wgrad_reduce_args a) {
   const int m = blockIdx.x, c0 = blockIdx.y * 32;
   const long long n_total = 64LL * a.cb;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;          // 8 warps
-  for (int tap = wrp; tap < 64; tap += 8) {
-    float acc = 0.f;
+  {
+    // a warp owns taps wrp, wrp + 8, ..., wrp + 56: eight independent accumulation streams, every split's eight loads in flight together
+    // (one tap at a time left 8 x ceil(ksplit / 8) dependent round trips per warp: 14-20 us per launch for 19 MB of L2-resident partials)
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
     const int c = c0 + lane;
     if (c < a.cb) {
-      const float* p = a.partials + (size_t)m * n_total + (size_t)tap * a.cb + c;
-      // eight splits in flight per round, added in split order (a rolled `acc += p[...]` loop waits out every load's latency in turn:
-      // 8 taps x 9 splits x ~600 clk = 23 us per launch for 19 MB -- profiles/r02c_launches_launches_wgan_gp.txt)
-      const size_t sstride = (size_t)a.m_pad * n_total;
-      for (int s0 = 0; s0 < a.ksplit; s0 += 8) {
+      const float* p = a.partials + (size_t)m * n_total + (size_t)wrp * a.cb + c;
+      const size_t sstride = (size_t)a.m_pad * n_total, tstride = (size_t)8 * a.cb;
+#pragma unroll 2
+      for (int s = 0; s < a.ksplit; ++s) {
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (s0 + u < a.ksplit) ? p[(size_t)(s0 + u) * sstride] : 0.f;
+        for (int u = 0; u < 8; ++u) v[u] = p[(size_t)s * sstride + (size_t)u * tstride];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += v[u];
+        for (int u = 0; u < 8; ++u) acc[u] += v[u];
       }
     }
-    tile[lane][tap] = acc * a.scale;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) tile[lane][wrp + 8 * u] = acc[u] * a.scale;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {

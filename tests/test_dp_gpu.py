@@ -62,3 +62,40 @@ def test_data_parallel_step(kind, mode, tmp_path):
     assert r['err'] == 0
     assert r['same'], 'replicas diverged: ' + r['note']
     assert r['worst'] < 2e-6, (r['worst'], r['note'])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_modules_survive_nn_dataparallel():
+    """The reference wraps its models in nn.DataParallel when it sees several GPUs (train_hybrid_progressive_gan.py:62-71).
+    Our modules must survive that wrapper unchanged: replicate() shallow-copies the module (the LinOp objects are shared, the parameters
+    of a replica are plain broadcast tensors without an optimizer arena), the scattered batch runs on both devices, the gradients are
+    reduced onto the original parameters.  Compared with the same modules run un-wrapped on the whole batch."""
+    from shapegan_b200 import config
+    from model.gan import Discriminator
+    from model.progressive_gan import Discriminator as ProgressiveDiscriminator
+    old = config.precision()
+    config.set_precision('fp32x')
+    try:
+        torch.manual_seed(3)
+        cases = [(Discriminator().cuda(0), torch.randn(4, 32, 32, 32).cuda(0) * 0.1)]
+        pd = ProgressiveDiscriminator().cuda(0)
+        pd.set_iteration(1)
+        cases.append((pd, torch.randn(4, 16, 16, 16).cuda(0) * 0.1))
+        for module, x in cases:
+            ref = module(x)
+            ref.sum().backward()
+            gref = [p.grad.detach().clone() for p in module.parameters() if p.grad is not None]
+            module.zero_grad(set_to_none=True)
+            par = torch.nn.DataParallel(module, device_ids=[0, 1])
+            if hasattr(module, 'iteration'):
+                par.module.set_iteration(1)
+            out = par(x)
+            assert out.shape == ref.shape
+            assert torch.allclose(out, ref, rtol=2e-3, atol=2e-4), (out - ref).abs().max()
+            out.sum().backward()
+            got = [p.grad.detach().clone() for p in module.parameters() if p.grad is not None]
+            assert len(got) == len(gref)
+            for a, b in zip(got, gref):
+                assert torch.allclose(a, b, rtol=5e-3, atol=5e-4 * float(b.abs().max() + 1e-6)), (a - b).abs().max()
+    finally:
+        config.set_precision(old)

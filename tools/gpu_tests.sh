@@ -1,4 +1,5 @@
 #!/bin/bash
+export SG_B200_NO_REBUILD=1     # the snapshot carries the library built in the dev container; never race nvcc across ranks
 # GPU visit: the whole -m gpu suite (parity errors recorded when "record" is passed) + smoke.  Args: [record] [pytest -k expression]
 mkdir -p gpurun_out
 T0=$(date +%s)
