@@ -21,12 +21,13 @@ void sg_count_launch() { ++g_launches; }
 __device__ int g_error_word = 0;
 
 int* sg_error_word() {
-  static int* ptr = nullptr;
-  if (!ptr) {
+  static int* ptr[64] = {};                    // the symbol has one instance per device
+  const int d = PerDevice::cur();
+  if (!ptr[d]) {
     void* p = nullptr;
-    if (cudaGetSymbolAddress(&p, g_error_word) == cudaSuccess) ptr = (int*)p;
+    if (cudaGetSymbolAddress(&p, g_error_word) == cudaSuccess) ptr[d] = (int*)p;
   }
-  return ptr;
+  return ptr[d];
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing

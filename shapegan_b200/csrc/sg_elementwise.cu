@@ -712,8 +712,8 @@ extern "C" int sg_col2im_c1(const void* P, int64_t p_ps, int planes, int n, int 
     if (planes == 1 && (w % 8) == 0 && (h % 4) == 0 && (d % 4) == 0 && ((uintptr_t)P & 15) == 0 && (long long)(d / 4) * n <= 65535 &&
         !(nt && nt[0] == '1')) {
       const size_t smem = 360 * kC2iPitchW * sizeof(uint32_t);
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(sg_col2im_c1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+      static PerDevice attr;
+      if (attr.first()) { cudaFuncSetAttribute(sg_col2im_c1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr.done(); }
       dim3 grid((unsigned)(w / 8), (unsigned)(h / 4), (unsigned)((d / 4) * n));
       sg_col2im_c1_tiled_kernel<<<grid, 256, smem, ST(stream)>>>((const bf16*)P, n, d, h, w, bias, act, out);
       SG_CUDA_CHECK_LAUNCH();

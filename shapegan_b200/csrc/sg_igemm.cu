@@ -1593,11 +1593,11 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
         uint32_t be[2] = {1, 1};
         if (brows >= (1ull << 31) || !tma_make_map(&q.tmB, a->b_packed, 2, bd, bs, bb, be, false)) q.b_tma = 0;
       }
-      static bool pattr_set = false;
-      if (!pattr_set) {
+      static PerDevice pattr;
+      if (pattr.first()) {
         cudaError_t e = cudaFuncSetAttribute(sg_igemm_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-        pattr_set = true;
+        pattr.done();
       }
       const int clusters = (int)std::min<long long>(q.work_total, sms / 2);
       sg_igemm_halo2_kernel<<<2 * clusters, kIgemmThreads, psmem, (cudaStream_t)stream>>>(q);
@@ -1609,11 +1609,11 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   }
   if (p.halo) {
     const size_t hsmem = halo_smem_plan(p, (unsigned)bn * 128u, a->out_kind == SG_OUT_BF16 && !split_ws);
-    static bool hattr_set = false;
-    if (!hattr_set) {
+    static PerDevice hattr;
+    if (hattr.first()) {
       cudaError_t e = cudaFuncSetAttribute(sg_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-      hattr_set = true;
+      hattr.done();
     }
     const int hgrid = (int)std::min<long long>(p.work_total, sms);
     sg_igemm_halo_kernel<<<hgrid, kIgemmThreads, hsmem, (cudaStream_t)stream>>>(p);
@@ -1624,11 +1624,11 @@ extern "C" int sg_igemm(const sg_igemm_args* a, void* stream) {
   }
   p.epi_off = plain_epi ? (unsigned)(kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes) : 0u;      // (the halo plans above overwrote it)
   const size_t smem = kSmemHeader + p.ktab_bytes + (size_t)stages * p.stage_bytes + plain_epi;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(sg_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
+    attr.done();
   }
   int grid = (int)std::min<long long>(p.work_total, sms);
   { const char* gg = getenv("SG_B200_IGEMM_GRID"); if (gg && atoi(gg) > 0) grid = std::min(grid, atoi(gg)); }   // measurement only

@@ -16,3 +16,16 @@ void sg_count_launch();                   // bookkeeping for bench.py's gpu_laun
     if (e__ != cudaSuccess) return sg::sg_fail((int)e__, cudaGetErrorString(e__)); \
     sg::sg_count_launch();                                            \
   } while (0)
+
+// Per-DEVICE one-time initialisation.  cudaFuncSetAttribute, __constant__ uploads and device-symbol addresses belong to the current
+// device, and one process may drive several (nn.DataParallel replicas run as threads of one process: train_hybrid_progressive_gan.py:62-71).
+// Usage:  static sg::PerDevice once;  if (once.first()) { ...; once.done(); }     (first() is true until done() was called on this device)
+namespace sg {
+struct PerDevice {
+  bool flag[64] = {};
+  static int cur() { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : 0; }
+  bool first() const { return !flag[cur()]; }
+  void done() { flag[cur()] = true; }
+};
+}  // namespace sg
+

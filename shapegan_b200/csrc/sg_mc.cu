@@ -183,12 +183,12 @@ __global__ void __launch_bounds__(kMcBlock) sg_mc_emit_faces_kernel(const McP p,
 using namespace sg;
 
 static int mc_upload_tables(cudaStream_t st) {
-  static bool done = false;
-  if (done) return 0;
+  static PerDevice once;
+  if (!once.first()) return 0;
   cudaError_t e = cudaMemcpyToSymbolAsync(c_mc_count, kMcTriCountHost, sizeof(kMcTriCountHost), 0, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_mc_edges, kMcTriEdgesHost, sizeof(kMcTriEdgesHost), 0, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-  done = true;
+  once.done();
   return 0;
 }
 

@@ -654,11 +654,11 @@ extern "C" int sg_sdfnet_fwd(const sg_sdfnet_fwd_args* a, void* stream) {
   p.pairs = (tiles + 1) / 2;
   p.err = sg_error_word();
   p.tma_stash = (p.stash != nullptr && sdf_stash_map(&p.tm_stash, p.stash, a->n)) ? 1 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
+    attr.done();
   }
   // biases / xyz columns / head -> constant bank (stream ordered, capturable; one SDFNet per stream at a time)
   cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_aux, a->aux, sizeof(float) * kAuxFloats, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
@@ -692,11 +692,11 @@ extern "C" int sg_sdfnet_infer(const sg_sdfnet_infer_args* a, void* stream) {
   const long long tiles = (a->n + kTileRows - 1) / kTileRows;
   p.pairs = (tiles + 1) / 2;
   p.err = sg_error_word();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfSmem);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
+    attr.done();
   }
   cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_aux, a->aux, sizeof(float) * kAuxFloats, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
@@ -726,12 +726,12 @@ extern "C" int sg_sdfnet_bwd(const sg_sdfnet_bwd_args* a, void* stream) {
   p.err = sg_error_word();
   p.gpoints = a->gpoints;
   p.tma_stash = (p.gstash != nullptr && sdf_stash_map(&p.tm_stash, p.gstash, a->n)) ? 1 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(sg_sdfnet_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfBwdSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sg_sdfnet_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdfBwdSmem);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
+    attr.done();
   }
   cudaError_t e = cudaMemcpyToSymbolAsync(c_sdf_w8, a->w8, sizeof(float) * 256, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));

@@ -525,12 +525,12 @@ extern "C" int sg_wgrad(const sg_wgrad_args* a, void* stream) {
     }
   }
   const size_t smem = kWgHeader + (size_t)p.stages * p.stage_bytes + 2048;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(sg_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sg_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return sg_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
+    attr.done();
   }
   const int sms = sg_num_sms();
   const char* no_pair = getenv("SG_B200_NO_WGRAD_PAIR");

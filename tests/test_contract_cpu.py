@@ -151,3 +151,35 @@ def test_sum_arena_slices_are_zeroed_disjoint_and_refreshed():
     assert arena.buf is not first                                   # exhausted arena replaced by a fresh zeroed one
     big = arena.take(arena.SIZE + 1, dev)
     assert big.numel() == arena.SIZE + 1 and big.abs().sum().item() == 0
+
+
+def test_splitk_plan_fills_the_machine():
+    """sg_igemm_plan (host logic only, no GPU): Conv3d(128->256) on 8^3 -> 4^3 has K = 8192 and few output tiles.  The library picks the
+    number of M sub-tiles per CTA together with the K split so that 148 SMs are as full as possible; the workspace it asks for says
+    which split it chose: B = 64 -> 32 tiles x 4 splits, B = 128 -> 64 x 2, B = 192 (the batched critic) -> 48 double tiles x 3 splits.
+    Layers with at least one wave of tiles are not split."""
+    import ctypes
+    from shapegan_b200 import _lib as L
+    lib = L.lib()
+
+    def plan(mode, b, r, cin, cout, k, out_dims=(0, 0, 0), classes=1):
+        a = L.SgIgemmArgs()
+        a.mode, a.planes = mode, 1
+        a.a = L.SgTensor(ctypes.c_void_p(256), 0, b, r, r, r, cin)
+        a.a2 = L.SgTensor(None, 0, 1, 1, 1, 1, 0)
+        a.rows = b * (r // 2) ** 3 if mode == L.MODE_CONV else b * r ** 3
+        a.k, a.n_pad, a.n_valid = k, cout, cout
+        a.b_packed, a.out = ctypes.c_void_p(256), ctypes.c_void_p(256)
+        a.out_kind, a.out_ld = L.OUT_BF16, cout
+        a.out_d, a.out_h, a.out_w = out_dims
+        n = ctypes.c_size_t(0)
+        L.check(lib.sg_igemm_plan(ctypes.byref(a), ctypes.byref(n)), 'sg_igemm_plan')
+        return n.value, a.rows * classes * cout * 4
+
+    for b, ks in ((64, 4), (128, 2), (192, 3)):
+        ws, slab = plan(L.MODE_CONV, b, 8, 128, 256, 64 * 128)
+        assert ws == ks * slab, (b, ws / slab)
+    ws, _ = plan(L.MODE_CONV, 64, 16, 64, 128, 64 * 64)                      # 256 tiles: more than one wave, no split
+    assert ws == 0
+    ws, slab = plan(L.MODE_CONVT, 64, 4, 256, 128, 8 * 256, out_dims=(8, 8, 8), classes=8)     # 8 classes x 32 tiles = 256 items: no split
+    assert ws == 0
