@@ -245,7 +245,8 @@ def test_wgrad(planes, merge_n):
 
 @pytest.mark.parametrize('planes', [1, 2])
 @pytest.mark.parametrize('mode,b,r,cin,cout,ks', [('conv', 8, 8, 128, 256, 0), ('conv', 5, 8, 128, 256, 3), ('convt', 3, 4, 256, 128, 2),
-                                                   ('conv', 2, 8, 64, 40, 4)])
+                                                   ('conv', 2, 8, 64, 40, 4),
+                                                   ('conv', 192, 8, 128, 256, 0)])     # the batched critic's D3: auto = two sub-tiles x 3 splits
 def test_splitk_partial_slabs(mode, b, r, cin, cout, ks, planes, monkeypatch):
     """Split-K through fp32 partial slabs + the finish kernel (bias, LeakyReLU, mask, bf16 hi/lo planes) against the same layer with
     SG_B200_NO_SPLITK=1: the shape class of Conv3d(128->256) 8^3 -> 4^3 (few output tiles x K = 8192).  ks = 0 is the auto policy."""
